@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_features():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "features_golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_fusion():
+    import numpy as np
+    return np.load(os.path.join(GOLDEN, "fusion_golden.npz"))
