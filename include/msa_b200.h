@@ -1,0 +1,124 @@
+/* msa_b200 — C ABI of the B200 (sm_100a) implementation of the audio-features -> fusion hot path.
+ *
+ * The reference (Joaonic/multimodal-sentiment-analyzer) has no FFI of its own: its boundary for
+ * this path is two Python classes.  Every entry point below names the reference interface it
+ * replaces (paths relative to the reference root); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name says host; buffers are caller-owned;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous
+ *     on that stream and never synchronise the device;
+ *   - return value: MSA_OK (0) or a negative MSA_ERR_* / positive cudaError_t; nothing throws
+ *     (the reference's convention is "never raise, return a default": the Python shim maps a
+ *     non-zero code to the reference's documented default AND logs it);
+ *   - one caller thread per stream; no internal threads; constant tables are built once per
+ *     device on first use (thread-safe).
+ */
+#ifndef MSA_B200_H
+#define MSA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSA_OK 0
+#define MSA_ERR_BAD_ARGUMENT (-1)
+#define MSA_ERR_UNSUPPORTED_LENGTH (-2) /* segment too long for one cluster's shared memory */
+#define MSA_ERR_NOT_PACKED (-3)
+#define MSA_ERR_WORKSPACE (-4)
+
+/* flags of msa_features_* */
+#define MSA_FEAT_STRICT_NAN 1 /* mono intensity = NaN exactly like audio_analyzer.py:194-196 (default) */
+#define MSA_FEAT_BULK_COPY 2  /* stage fp32 slices with TMA bulk copies (cp.async.bulk) */
+/* parts mask: which feature groups to compute (the rest take the reference's exception defaults) */
+#define MSA_PART_WAVE 1  /* rhythm, speech_rate, snr, consistency */
+#define MSA_PART_MFCC 2  /* timbre, clarity */
+#define MSA_PART_PITCH 4 /* STFT-512 -> ISTFT residual */
+#define MSA_PART_ALL 7
+
+#define MSA_DETAIL_STRIDE 96
+
+int msa_version(void);
+const char* msa_strerror(int code);
+
+/* Number of CTAs per cluster msa_features_* will use for segments of T samples (0 if T is
+ * unsupported), and the dynamic shared memory per CTA.  For capacity planning / tests. */
+int msa_features_cluster_size(int T);
+int msa_features_smem_bytes(int T, int cluster_size);
+
+/* Batched AudioAnalyzer feature body: B independent mono segments of T samples each.
+ * Replaces, per segment, audio_analyzer.py:89-131 (_analyze_pitch :175-188, _analyze_intensity
+ * :190-201, _analyze_timbre :203-217, _analyze_speech_rate :219-233, _analyze_rhythm :235-263,
+ * _calculate_audio_quality/_signal_noise_ratio/_clarity/_consistency :265-329), the
+ * AudioFeatureNormalizer (src/utils/normalization.py:26-44) and the audio-row assembly +
+ * nan_to_num of streaming_processor.py:250-268, 295-298.
+ *
+ *   wav     [B, T] fp32 in [-1, 1] (torchaudio.load layout, one channel)        (device)
+ *   emo8    [B, 8] output of _analyze_emotion (out of scope: wav2vec2), or NULL = uniform 1/8
+ *   feat31  [B, 31] out: LayerNorm31(raw27)[:27] ++ [audio_quality, snr, clarity, consistency],
+ *           NaN -> 0 (the row AdvancedFusionModel.forward receives as audio_probs)
+ *   detail  [B, 96] out or NULL: [0:27] raw features before LayerNorm in analyze()'s concat order
+ *           (emotion8, pitch, intensity, timbre13, speech_rate, rhythm3), [27:31] the four quality
+ *           floats, [32:63] the full LayerNorm(31) row (NaN where the reference is NaN),
+ *           [64:75] diagnostics (top_db max, residual mean/std/max, energies, counts)
+ *   dbg_mfcc [B, T/200+1, 13] out or NULL: the MFCC matrix (frames x coefficients)
+ *   cluster_size 0 = auto (msa_features_cluster_size), else 1/2/4/8/16
+ */
+int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
+                     float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream);
+
+/* Same, from int16 PCM (pcm_s16le as written by offline_processor.py:87-91 and
+ * streaming_processor.py:185-196); samples are scaled by 1/32768 like torchaudio.load. */
+int msa_features_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail,
+                     float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream);
+
+/* ---- fusion model (src/models/fusion_model.py) ------------------------------------------- */
+
+/* Size in bytes of the packed-weight blob and of the activation workspace for batch B. */
+size_t msa_fusion_packed_bytes(void);
+size_t msa_fusion_workspace_bytes(int B);
+
+/* Repack an AdvancedFusionModel state_dict (fusion_model.py:44-103) into the
+ * device layout the kernels read.  `tensors` is a HOST array of 42 HOST fp32 pointers in the
+ * order msa_fusion_tensor_name(i) gives; `packed` is a DEVICE buffer of msa_fusion_packed_bytes().
+ * Synchronous (done once per checkpoint load, fusion_model.py:259-294). */
+int msa_fusion_num_tensors(void);
+const char* msa_fusion_tensor_name(int i);
+size_t msa_fusion_tensor_numel(int i);
+int msa_fusion_pack(const float* const* tensors_host, void* packed_dev, void* stream);
+
+/* AdvancedFusionModel.forward in eval mode (fusion_model.py:131-190):
+ *   face [B,27], audio [B,31], text [B,783] or NULL.  Supported: all three (_fuse_all, :386-408)
+ *   and face+audio (_fuse_face_audio, :296-321).  Every other combination never produces a
+ *   "fused" tensor in the reference (pass-through / always-raising pairs); the Python shim
+ *   reproduces those dict results without calling the device.
+ *   logits7 [B,7] out (the reference's "fused": raw logits, no softmax), argmax [B] int32 out or NULL.
+ */
+int msa_fusion_forward(const float* face, const float* audio, const float* text, int B, const void* packed,
+                       void* workspace, size_t workspace_bytes, float* logits7, int32_t* argmax, void* stream);
+
+/* Select the implementation behind msa_fusion_forward: 0 = tcgen05 tensor-core kernels (default),
+ * 1 = fp32 CUDA-core bring-up kernels kept as an on-device cross-check (tests only; also selectable
+ * with MSA_FUSION_IMPL=simt).  Same ABI, same results to fp32 rounding. */
+int msa_fusion_set_impl(int impl);
+
+/* ---- speaker / timeline aggregation (src/processors/offline_processor.py:259-298) --------- */
+
+/* label [S] int32 = argmax of the fused logits per segment (in segment order), speaker [S] int32 in
+ * [0, n_speakers).  hist [n_speakers,7] out: label counts; dominant [n_speakers] out: mode of the
+ * labels (:287-290, ties -> smallest label, -1 if the speaker has no segment); run3 [S] out: 1 where
+ * a segment starts three equal consecutive labels within its speaker's own sequence (:293-298). */
+int msa_aggregate_speakers(const int32_t* label, const int32_t* speaker, int S, int n_speakers, int32_t* hist,
+                           int32_t* dominant, int32_t* run3, void* stream);
+
+/* Number of kernel launches the last call of each kind issued on this thread (bench accounting). */
+int msa_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSA_B200_H */

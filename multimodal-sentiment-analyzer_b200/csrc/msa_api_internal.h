@@ -1,0 +1,10 @@
+// Internal helpers shared by the translation units of libmsa_b200.so.
+#pragma once
+#include "../../include/msa_b200.h"
+
+namespace msa {
+constexpr int kFeatThreads = 256;
+constexpr int kMaxSmem = 232448;   // 227 KB opt-in shared memory per CTA on sm_100
+void reset_launches();
+void note_launches(int n);
+}  // namespace msa

@@ -1,0 +1,148 @@
+// Launch side of the fused audio-feature kernel (see msa_features_body.cuh for the algorithm).
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "msa_api_internal.h"
+#include "msa_env_gpu.cuh"
+
+namespace msa {
+
+template <class InT>
+__global__ void __launch_bounds__(kFeatThreads, 1) features_kernel(const FeatParams P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  GpuEnv env;
+  env.tid = threadIdx.x;
+  env.nthreads = blockDim.x;
+  env.lane = threadIdx.x & 31;
+  env.nlanes = 32;
+  env.warp = threadIdx.x >> 5;
+  env.nwarps = blockDim.x >> 5;
+  env.rank = (int)cluster.block_rank();
+  env.nranks = (int)cluster.num_blocks();
+  env.cluster_id = blockIdx.x / env.nranks;
+  features_cta<GpuEnv, InT>(env, P, smem);
+}
+
+static std::mutex g_tab_mutex;
+static FeatureTables* g_tab_dev[64] = {nullptr};
+
+static int get_tables(const FeatureTables** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return MSA_ERR_BAD_ARGUMENT;
+  std::lock_guard<std::mutex> lock(g_tab_mutex);
+  if (!g_tab_dev[dev]) {
+    static FeatureTables host;
+    build_feature_tables(host);
+    FeatureTables* d = nullptr;
+    e = cudaMalloc(&d, sizeof(FeatureTables));
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMemcpy(d, &host, sizeof(FeatureTables), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return (int)e; }
+    g_tab_dev[dev] = d;
+  }
+  *out = g_tab_dev[dev];
+  return MSA_OK;
+}
+
+static int slice_len_for(int T, int c) {
+  int L = (T + c - 1) / c;
+  return ((L + kAtom - 1) / kAtom) * kAtom;
+}
+
+int features_cluster_size(int T) {
+  if (T < 1) return 0;
+  const int nwarps = kFeatThreads / 32;
+  // prefer slices of <= 20000 samples (5 s -> 4 CTAs); grow the cluster while a slice does not fit
+  for (int c = 1; c <= 16; c *= 2) {
+    const int L = slice_len_for(T, c);
+    if (L <= 20000 && feat_layout(L, nwarps).total <= kMaxSmem) return c;
+  }
+  for (int c = 1; c <= 16; c *= 2)
+    if (feat_layout(slice_len_for(T, c), nwarps).total <= kMaxSmem) return c;
+  return 0;
+}
+
+int features_smem_bytes(int T, int c) {
+  if (T < 1 || c < 1) return 0;
+  return feat_layout(slice_len_for(T, c), kFeatThreads / 32).total;
+}
+
+template <class InT>
+static int launch_features(const InT* wav, int B, int T, const float* emo8, float* feat31, float* detail,
+                           float* dbg_mfcc, int flags, int parts, int cluster_size, cudaStream_t stream) {
+  if (!wav || !feat31 || B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
+  if (B == 0) return MSA_OK;
+  int c = cluster_size ? cluster_size : features_cluster_size(T);
+  if (c != 1 && c != 2 && c != 4 && c != 8 && c != 16) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
+  // torch.stft's reflect padding needs T > n_fft/2: below that the reference's method raises and
+  // returns its default, which is what a cleared part bit produces.
+  if (T <= kNfftP / 2) parts &= ~kPartPitch;
+  if (T <= kNfftM / 2) parts &= ~kPartMfcc;
+  const FeatureTables* tab = nullptr;
+  int rc = get_tables(&tab);
+  if (rc != MSA_OK) return rc;
+
+  FeatParams P{};
+  P.wav = wav;
+  P.is_s16 = sizeof(InT) == 2;
+  P.B = B;
+  P.T = T;
+  P.slice_len = slice_len_for(T, c);
+  P.noise_n = (int)(0.05 * (double)T);   // int(0.05 * waveform.shape[1]), audio_analyzer.py:282
+  P.emo8 = emo8;
+  P.feat31 = feat31;
+  P.detail = detail;
+  P.dbg_mfcc = dbg_mfcc;
+  P.tab = tab;
+  P.flags = flags;
+  P.parts = parts;
+  const FeatLayout lay = feat_layout(P.slice_len, kFeatThreads / 32);
+  if (lay.total > kMaxSmem) return MSA_ERR_UNSUPPORTED_LENGTH;
+
+  auto kern = features_kernel<InT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
+  if (e != cudaSuccess) return (int)e;
+  if (c > 8) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)B * c, 1, 1);
+  cfg.blockDim = dim3(kFeatThreads, 1, 1);
+  cfg.dynamicSmemBytes = lay.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = c;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  e = cudaLaunchKernelEx(&cfg, kern, P);
+  if (e != cudaSuccess) return (int)e;
+  note_launches(1);
+  return MSA_OK;
+}
+
+}  // namespace msa
+
+extern "C" int msa_features_cluster_size(int T) { return msa::features_cluster_size(T); }
+extern "C" int msa_features_smem_bytes(int T, int c) { return msa::features_smem_bytes(T, c); }
+
+extern "C" int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
+                                float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream) {
+  msa::reset_launches();
+  return msa::launch_features<float>(wav, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" int msa_features_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail,
+                                float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream) {
+  msa::reset_launches();
+  return msa::launch_features<int16_t>(pcm, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size,
+                                       (cudaStream_t)stream);
+}

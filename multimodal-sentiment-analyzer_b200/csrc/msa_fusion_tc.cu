@@ -1,0 +1,541 @@
+// Tensor-core path of AdvancedFusionModel.forward: every Linear(+LayerNorm+ReLU) of
+// fusion_model.py:44-98 as ONE warp-specialised tcgen05 kernel per layer.
+//
+//   Y = ReLU(LayerNorm(X W^T + b))          X: [B, K] split-bf16 (hi + lo), W: [N, K] split-bf16
+//
+// Precision: plain bf16 operands fail the parity bar (99.58 % argmax agreement),
+// so each product is issued as three bf16 MMAs with fp32 accumulation in tensor memory:
+//   X W^T ~= Xhi Whi^T + Xlo Whi^T + Xhi Wlo^T      (relative error ~2^-16)
+//
+// Kernel shape: one CTA owns 128 rows x 512 output columns = the whole 128-lane x 512-column
+// tensor memory, so the LayerNorm statistics of a 512-wide layer are thread-local in the
+// epilogue (thread <-> TMEM lane <-> row).  1024-wide layers run as a 2-CTA cluster (one half of
+// the columns each) that exchanges per-row (sum, sum of squares) through distributed shared
+// memory.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue.  Operands are staged by TMA into 128-byte-swizzled K-major tiles.
+#include <cooperative_groups.h>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "msa_api_internal.h"
+#include "msa_fusion_common.cuh"
+
+namespace msa {
+namespace cg = cooperative_groups;
+
+constexpr int BLOCK_M = 128, BLOCK_K = 64, N_SUB = 256, N_CTA = 512;
+constexpr int kStages = 2;
+constexpr int kTileA = BLOCK_M * BLOCK_K * 2;            // 16 KB
+constexpr int kTileW = N_SUB * BLOCK_K * 2;              // 32 KB
+constexpr int kStageBytes = 2 * kTileA + 2 * kTileW;     // 96 KB: A_hi, A_lo, W_hi, W_lo
+constexpr int kTcThreads = 256;
+constexpr uint32_t kSpinLimit = 400u * 1000u * 1000u;    // a lost barrier traps instead of hanging the GPU
+
+struct TcTail {            // smem after the stages
+  uint64_t full[kStages], empty[kStages], accum_full;
+  uint32_t tmem_base, pad;
+  float2 stats[BLOCK_M];
+  float bias[N_CTA], gamma[N_CTA], beta[N_CTA];
+  float w8[kOut * N_CTA];  // final layer only
+  float b8[8];
+};
+constexpr int kTcSmemBytes = kStages * kStageBytes + (int)sizeof(TcTail) + 1024;
+
+struct TcEpilogue {
+  const float* bias;       // [n_total]
+  const float* gamma;      // LayerNorm weight [n_total]
+  const float* beta;
+  __nv_bfloat16* out_hi;   // [rows, ld_out] at col_off
+  __nv_bfloat16* out_lo;
+  int ld_out, col_off;
+  int n_total;             // 512 or 1024
+  int m_valid;             // B
+  int k_blocks;            // Kpad / 64
+  // final layer (kFinal): Linear(512 -> 7) fused after the ReLU
+  const float* w8;
+  const float* b8;
+  float* logits;
+  int32_t* argmax;
+};
+
+__device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = s2u(bar);
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!ok && ++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s2u(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(s2u(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, 128-byte swizzle: 8-row groups of 1024 bytes (SBO), one swizzle atom along K (LBO unused)
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((s2u(smem_ptr) >> 4) & 0x3FFF);        // start address, bits [0,14)
+  d |= (uint64_t)(1024 >> 4) << 32;                      // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// kPair: 2-CTA cluster along grid.y (n_total = 1024). kFinal: fuse Linear(512 -> 7) + argmax.
+template <bool kPair, bool kFinal>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_linear_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcEpilogue ep) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TcTail* tail = reinterpret_cast<TcTail*>(smem + kStages * kStageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * N_CTA;
+  const int k_blocks = ep.k_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
+    mbar_init(&tail->accum_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&tail->tmem_base)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tail->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ns = 0; ns < N_CTA / N_SUB; ++ns) {
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&tail->empty[stage], phase ^ 1);
+          unsigned char* st = smem + stage * kStageBytes;
+          mbar_expect_tx(&tail->full[stage], kStageBytes);
+          tma_load_2d(&tmA_hi, &tail->full[stage], st, kb * BLOCK_K, m0);
+          tma_load_2d(&tmA_lo, &tail->full[stage], st + kTileA, kb * BLOCK_K, m0);
+          tma_load_2d(&tmW_hi, &tail->full[stage], st + 2 * kTileA, kb * BLOCK_K, n0 + ns * N_SUB);
+          tma_load_2d(&tmW_lo, &tail->full[stage], st + 2 * kTileA + kTileW, kb * BLOCK_K, n0 + ns * N_SUB);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      // kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = 256
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_SUB >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int ns = 0; ns < N_CTA / N_SUB; ++ns) {
+        const uint32_t tmem_d = tmem_base + ns * N_SUB;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&tail->full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          unsigned char* st = smem + stage * kStageBytes;
+          const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileA);
+          const uint64_t w_hi = umma_desc_sw128(st + 2 * kTileA), w_lo = umma_desc_sw128(st + 2 * kTileA + kTileW);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);          // 32 bytes per K step inside the swizzle atom
+            umma_bf16(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
+            umma_bf16(tmem_d, a_lo + adv, w_hi + adv, idesc, 1);
+            umma_bf16(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
+          }
+          umma_commit(&tail->empty[stage]);                              // frees the smem stage when the MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+      umma_commit(&tail->accum_full);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue: thread <-> row
+    const int q = warp & 3;
+    const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 128;
+    for (int i = et; i < N_CTA; i += 128) {
+      tail->bias[i] = ep.bias[n0 + i];
+      tail->gamma[i] = ep.gamma[n0 + i];
+      tail->beta[i] = ep.beta[n0 + i];
+    }
+    if (kFinal) {
+      for (int i = et; i < kOut * N_CTA; i += 128) tail->w8[i] = ep.w8[i];
+      if (et < kOut) tail->b8[et] = ep.b8[et];
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");                       // epilogue warps only
+    mbar_wait(&tail->accum_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float sum = 0.0f, sumsq = 0.0f;
+    for (int c = 0; c < N_CTA; c += 32) {
+      float v[32];
+      tmem_ld32(trow + c, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = v[i] + tail->bias[c + i];
+        sum += x;
+        sumsq = fmaf(x, x, sumsq);
+      }
+    }
+    tail->stats[row_in_tile] = make_float2(sum, sumsq);
+  }
+
+  if (kPair) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();                                                      // both halves' row statistics are published
+    if (warp >= 4) {
+      const int row_in_tile = (warp & 3) * 32 + lane;
+      const float2* peer = cluster.map_shared_rank(&tail->stats[0], cluster.block_rank() ^ 1);
+      const float2 o = peer[row_in_tile];
+      float2 mine = tail->stats[row_in_tile];
+      mine.x += o.x;
+      mine.y += o.y;
+      // merged statistics stay in registers (stats[] is not overwritten: the peer may still be reading it)
+      const float mean = mine.x / (float)ep.n_total;
+      const float var = fmaxf(mine.y / (float)ep.n_total - mean * mean, 0.0f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      // second pass
+      const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const int row = m0 + row_in_tile;
+      for (int c = 0; c < N_CTA; c += 32) {
+        float v[32];
+        tmem_ld32(trow + c, v);
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float y0 = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
+          float y1 = (v[i + 1] + tail->bias[c + i + 1] - mean) * rstd * tail->gamma[c + i + 1] + tail->beta[c + i + 1];
+          y0 = fmaxf(y0, 0.0f);
+          y1 = fmaxf(y1, 0.0f);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+          hi[i / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          lo[i / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        if (row < ep.m_valid) {
+          const size_t o = (size_t)row * ep.ld_out + ep.col_off + n0 + c;
+          uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
+          uint4* pl = reinterpret_cast<uint4*>(ep.out_lo + o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster.sync();                                                      // the peer has finished reading my statistics
+  } else {
+    if (warp >= 4) {
+      const int row_in_tile = (warp & 3) * 32 + lane;
+      const float2 mine = tail->stats[row_in_tile];
+      const float mean = mine.x / (float)ep.n_total;
+      const float var = fmaxf(mine.y / (float)ep.n_total - mean * mean, 0.0f);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const int row = m0 + row_in_tile;
+      float acc[kOut];
+#pragma unroll
+      for (int j = 0; j < kOut; ++j) acc[j] = 0.0f;
+      for (int c = 0; c < N_CTA; c += 32) {
+        float v[32];
+        tmem_ld32(trow + c, v);
+        if (kFinal) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float y = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
+            y = fmaxf(y, 0.0f);
+#pragma unroll
+            for (int j = 0; j < kOut; ++j) acc[j] = fmaf(y, tail->w8[j * N_CTA + c + i], acc[j]);
+          }
+        } else {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float y0 = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
+            float y1 = (v[i + 1] + tail->bias[c + i + 1] - mean) * rstd * tail->gamma[c + i + 1] + tail->beta[c + i + 1];
+            y0 = fmaxf(y0, 0.0f);
+            y1 = fmaxf(y1, 0.0f);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+            hi[i / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[i / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          if (row < ep.m_valid) {
+            const size_t o = (size_t)row * ep.ld_out + ep.col_off + n0 + c;
+            uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
+            uint4* pl = reinterpret_cast<uint4*>(ep.out_lo + o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        }
+      }
+      if (kFinal && row < ep.m_valid) {
+        int best = 0;
+        float bv = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kOut; ++j) {
+          const float l = acc[j] + tail->b8[j];
+          ep.logits[(size_t)row * kOut + j] = l;
+          if (j == 0 || l > bv) { bv = l; best = j; }
+        }
+        if (ep.argmax) ep.argmax[row] = best;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------ input LayerNorm + split
+// One warp per row and modality: y = LN(x) * gamma + beta -> (hi, lo) bf16, K zero-padded; rows >= B zeroed.
+struct PrepArgs {
+  const float* x[3];
+  const float* gamma[3];
+  const float* beta[3];
+  __nv_bfloat16* hi[3];
+  __nv_bfloat16* lo[3];
+  int d[3], kpad[3];
+  int B, Bp, nmod;
+};
+
+__global__ void __launch_bounds__(256) tc_input_prep_kernel(const PrepArgs a) {
+  const int m = blockIdx.y;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= a.Bp) return;
+  const int d = a.d[m], kpad = a.kpad[m];
+  __nv_bfloat16* hi = a.hi[m] + (size_t)row * kpad;
+  __nv_bfloat16* lo = a.lo[m] + (size_t)row * kpad;
+  if (row >= a.B) {
+    for (int c = lane; c < kpad; c += 32) { hi[c] = __float2bfloat16_rn(0.0f); lo[c] = __float2bfloat16_rn(0.0f); }
+    return;
+  }
+  const float* x = a.x[m] + (size_t)row * d;
+  float v[25];                                                           // 783 <= 25 * 32
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 25; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < d) ? x[c] : 0.0f;
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)d;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 25; ++i) {
+    const int c = lane + 32 * i;
+    const float dd = (c < d) ? v[i] - mean : 0.0f;
+    sq = fmaf(dd, dd, sq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < 26; ++i) {
+    const int c = lane + 32 * i;
+    if (c < kpad) {
+      float y = 0.0f;
+      if (c < d) y = (v[i < 25 ? i : 24] - mean) * rstd * a.gamma[m][c] + a.beta[m][c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(y);
+      hi[c] = h;
+      lo[c] = __float2bfloat16_rn(y - __bfloat162float(h));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 row-major [rows, cols] -> TMA map with box [box_rows, 64 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return MSA_ERR_BAD_ARGUMENT;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MSA_OK : 1000 + (int)r;
+}
+
+struct LayerLaunch {
+  const void *a_hi, *a_lo; int a_cols;           // activations [Bp, a_cols]
+  int gemm;                                      // weight id
+  int bias_t, gamma_t, beta_t;                   // tensor ids
+  void *out_hi, *out_lo; int ld_out, col_off;
+  bool final_layer;
+};
+
+static int launch_layer(const LayerLaunch& L, int B, int Bp, const unsigned char* packed, const PackedHeader& h, float* logits,
+                        int32_t* argmax, cudaStream_t s) {
+  const GemmWeight& gw = kGemmWeights[L.gemm];
+  CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
+  int rc;
+  if ((rc = make_map(&mA_hi, L.a_hi, Bp, L.a_cols, BLOCK_M))) return rc;
+  if ((rc = make_map(&mA_lo, L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
+  if ((rc = make_map(&mW_hi, packed + h.hi_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
+  if ((rc = make_map(&mW_lo, packed + h.lo_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
+  TcEpilogue ep{};
+  ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
+  ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
+  ep.beta = reinterpret_cast<const float*>(packed + h.f32_off[L.beta_t]);
+  ep.out_hi = static_cast<__nv_bfloat16*>(L.out_hi);
+  ep.out_lo = static_cast<__nv_bfloat16*>(L.out_lo);
+  ep.ld_out = L.ld_out;
+  ep.col_off = L.col_off;
+  ep.n_total = gw.N;
+  ep.m_valid = B;
+  ep.k_blocks = gw.Kpad / BLOCK_K;
+  ep.w8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_W]);
+  ep.b8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_B]);
+  ep.logits = logits;
+  ep.argmax = argmax;
+
+  const bool pair = gw.N == 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(Bp / BLOCK_M, gw.N / N_CTA, 1);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = kTcSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = pair ? 2 : 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e;
+  if (pair) {
+    cudaFuncSetAttribute(tc_linear_ln_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<true, false>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
+  } else if (L.final_layer) {
+    cudaFuncSetAttribute(tc_linear_ln_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, true>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
+  } else {
+    cudaFuncSetAttribute(tc_linear_ln_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, false>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
+  }
+  if (e != cudaSuccess) return (int)e;
+  note_launches(1);
+  return MSA_OK;
+}
+
+int fusion_forward_tc(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
+                      const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
+                      cudaStream_t s) {
+  const bool three = text != nullptr;
+  const int Bp = wl.Bp;
+  auto f32 = [&](int t) { return reinterpret_cast<const float*>(packed + h.f32_off[t]); };
+  auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
+
+  PrepArgs pa{};
+  pa.x[0] = face; pa.x[1] = audio; pa.x[2] = text;
+  pa.gamma[0] = f32(T_FACE_NORM_W); pa.beta[0] = f32(T_FACE_NORM_B);
+  pa.gamma[1] = f32(T_AUDIO_NORM_W); pa.beta[1] = f32(T_AUDIO_NORM_B);
+  pa.gamma[2] = f32(T_TEXT_NORM_W); pa.beta[2] = f32(T_TEXT_NORM_B);
+  pa.hi[0] = bf(wl.x_face_hi); pa.lo[0] = bf(wl.x_face_lo);
+  pa.hi[1] = bf(wl.x_audio_hi); pa.lo[1] = bf(wl.x_audio_lo);
+  pa.hi[2] = bf(wl.x_text_hi); pa.lo[2] = bf(wl.x_text_lo);
+  pa.d[0] = kFaceDim; pa.d[1] = kAudioDim; pa.d[2] = kTextDim;
+  pa.kpad[0] = kFaceK; pa.kpad[1] = kAudioK; pa.kpad[2] = kTextK;
+  pa.B = B; pa.Bp = Bp; pa.nmod = three ? 3 : 2;
+  tc_input_prep_kernel<<<dim3((Bp + 7) / 8, pa.nmod), 256, 0, s>>>(pa);
+  note_launches(1);
+
+  const int cat_w = three ? 1536 : 1024;
+  const size_t xin_hi[3] = {wl.x_face_hi, wl.x_audio_hi, wl.x_text_hi}, xin_lo[3] = {wl.x_face_lo, wl.x_audio_lo, wl.x_text_lo};
+  const int xk[3] = {kFaceK, kAudioK, kTextK};
+  const int proj_g[3] = {G_FACE_PROJ, G_AUDIO_PROJ, G_TEXT_PROJ}, proj_b[3] = {T_FACE_PROJ_B, T_AUDIO_PROJ_B, T_TEXT_PROJ_B};
+  const int l0w[3] = {T_FACE_P0_W, T_AUDIO_P0_W, T_TEXT_P0_W}, l0b[3] = {T_FACE_P0_B, T_AUDIO_P0_B, T_TEXT_P0_B};
+  const int p3_g[3] = {G_FACE_P3, G_AUDIO_P3, G_TEXT_P3}, p3_b[3] = {T_FACE_P3_B, T_AUDIO_P3_B, T_TEXT_P3_B};
+  const int l4w[3] = {T_FACE_P4_W, T_AUDIO_P4_W, T_TEXT_P4_W}, l4b[3] = {T_FACE_P4_B, T_AUDIO_P4_B, T_TEXT_P4_B};
+  int rc;
+  for (int m = 0; m < pa.nmod; ++m) {
+    LayerLaunch p{bf(xin_hi[m]), bf(xin_lo[m]), xk[m], proj_g[m], proj_b[m], l0w[m], l0b[m], bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, 0, false};
+    if ((rc = launch_layer(p, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+    LayerLaunch q{bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, p3_g[m], p3_b[m], l4w[m], l4b[m], bf(wl.cat_hi), bf(wl.cat_lo), cat_w, m * kHalf, false};
+    if ((rc = launch_layer(q, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  }
+  LayerLaunch f0{bf(wl.cat_hi), bf(wl.cat_lo), cat_w, three ? G_FUS0 : G_FUS2, three ? T_FUS0_B : T_FUS2_B, T_FUS1_W, T_FUS1_B,
+                 bf(wl.f1_hi), bf(wl.f1_lo), kHidden, 0, false};
+  if ((rc = launch_layer(f0, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  LayerLaunch f4{bf(wl.f1_hi), bf(wl.f1_lo), kHidden, G_FUS4, T_FUS4_B, T_FUS5_W, T_FUS5_B, nullptr, nullptr, 0, 0, true};
+  if ((rc = launch_layer(f4, B, Bp, packed, h, logits7, argmax, s))) return rc;
+  return (int)cudaGetLastError();
+}
+
+}  // namespace msa

@@ -1,0 +1,104 @@
+"""Batched segment pipeline: audio features -> fusion -> per-segment result rows, sharded over the
+GPUs of one box, gathered, and aggregated per speaker.
+
+This is the data-parallel loop of /root/reference/src/processors/offline_processor.py:255-257
+(``for segment in segments: process_segment(...)``) and its speaker grouping (:259-298), with the
+per-segment body of streaming_processor.py:250-320 (audio row -> nan_to_num -> fusion -> argmax).
+
+Sharding: segments are independent, so rank r of N takes the contiguous range
+``shard_range(S, N, r)``, runs the same two kernels on its slice, and ONE collective
+(``all_gather`` of 40 x 32-bit words per segment over NCCL) assembles the result table; there is
+no other exchange on the data path.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .audio_analyzer import AudioAnalyzer
+from .fusion_model import AdvancedFusionModel
+
+ROW_WORDS = 40          # audio row 31 | logits 7 | argmax | segment id  (160 bytes / segment)
+
+
+def shard_range(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [begin, end) of rank `rank`: sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def pack_rows(audio_row: torch.Tensor, logits: torch.Tensor, argmax: torch.Tensor, first_id: int) -> torch.Tensor:
+    """[n, 40] fp32 result table; the two integer columns are stored bit-exactly (int32 viewed as fp32)."""
+    n = audio_row.shape[0]
+    rows = torch.empty(n, ROW_WORDS, device=audio_row.device, dtype=torch.float32)
+    rows[:, 0:31] = audio_row
+    rows[:, 31:38] = logits
+    ints = rows.view(torch.int32)
+    ints[:, 38] = argmax.to(torch.int32)
+    ints[:, 39] = torch.arange(first_id, first_id + n, device=audio_row.device, dtype=torch.int32)
+    return rows
+
+
+def unpack_rows(rows: torch.Tensor) -> Dict[str, torch.Tensor]:
+    ints = rows.view(torch.int32)
+    return {"audio_row": rows[:, 0:31], "logits": rows[:, 31:38], "argmax": ints[:, 38], "segment_id": ints[:, 39]}
+
+
+def gather_rows(local_rows: torch.Tensor, n_total: int, world_size: int, rank: int, group=None) -> torch.Tensor:
+    """The only collective of the path: all_gather of the per-rank result tables (ragged shards are
+    padded to the largest shard and trimmed after the gather).  world_size 1 is a no-op."""
+    if world_size == 1:
+        return local_rows
+    import torch.distributed as dist
+    sizes = [shard_range(n_total, world_size, r)[1] - shard_range(n_total, world_size, r)[0] for r in range(world_size)]
+    cap = max(sizes)
+    buf = torch.zeros(cap, ROW_WORDS, device=local_rows.device, dtype=torch.float32)
+    buf[: local_rows.shape[0]] = local_rows
+    out = torch.empty(world_size * cap, ROW_WORDS, device=local_rows.device, dtype=torch.float32)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return torch.cat([out[r * cap: r * cap + sizes[r]] for r in range(world_size)], dim=0)
+
+
+def aggregate_speakers(argmax: torch.Tensor, speaker: torch.Tensor, n_speakers: int) -> Dict[str, torch.Tensor]:
+    """offline_processor.py:259-298 on device: per-speaker label histogram, dominant emotion (mode)
+    and the starts of three-in-a-row "patterns" within each speaker's own segment sequence."""
+    dev = argmax.device
+    a = argmax.to(torch.int32).contiguous()
+    s = speaker.to(dev, torch.int32).contiguous()
+    S = a.shape[0]
+    hist = torch.empty(n_speakers, 7, device=dev, dtype=torch.int32)
+    dom = torch.empty(n_speakers, device=dev, dtype=torch.int32)
+    run3 = torch.zeros(max(S, 1), device=dev, dtype=torch.int32)
+    rc = _lib.lib().msa_aggregate_speakers(_lib.ptr(a), _lib.ptr(s), S, n_speakers, _lib.ptr(hist), _lib.ptr(dom), _lib.ptr(run3),
+                                           _lib.current_stream_ptr(dev))
+    _lib.check(rc, "msa_aggregate_speakers")
+    return {"hist": hist, "dominant": dom, "run3": run3[:S]}
+
+
+class SegmentPipeline:
+    """features -> fusion for a batch of segments on one GPU (one rank)."""
+
+    def __init__(self, analyzer: AudioAnalyzer, fusion: AdvancedFusionModel):
+        self.analyzer = analyzer
+        self.fusion = fusion
+        self.device = analyzer.device
+
+    @torch.no_grad()
+    def run(self, waves: torch.Tensor, face: torch.Tensor, text: Optional[torch.Tensor] = None,
+            emotion_probs: Optional[torch.Tensor] = None, first_id: int = 0) -> torch.Tensor:
+        """waves [n, T] (fp32 or int16 PCM), face [n, 27], text [n, 783] or None (the live streaming
+        path has no text, streaming_processor.py:420-424) -> result table [n, 40]."""
+        audio_row = self.analyzer.analyze_batch(waves, emotion_probs)
+        logits, amax = self.fusion.fused_with_argmax(face, audio_row, text)
+        return pack_rows(audio_row, logits, amax, first_id)
+
+    @torch.no_grad()
+    def run_sharded(self, waves_local, face_local, text_local, n_total: int, world_size: int, rank: int,
+                    emotion_probs=None, group=None) -> torch.Tensor:
+        """This rank's shard through the pipeline, then the single result gather."""
+        begin, _ = shard_range(n_total, world_size, rank)
+        rows = self.run(waves_local, face_local, text_local, emotion_probs, first_id=begin)
+        return gather_rows(rows, n_total, world_size, rank, group)

@@ -1,0 +1,114 @@
+"""CPU emulation of the fused CUDA feature kernel vs the oracle.
+
+tests/emu/emu_features.cpp compiles the SAME kernel body the GPU runs
+(csrc/msa_features_body.cuh) with g++ and executes one cluster per segment on OS
+threads.  This checks the slice / halo / ownership / overlap-add / digit-reversal
+logic without a GPU; the GPU parity tests proper are tests/test_gpu_*.py.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import features_np as fx
+from oracle import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "emu", "emu_features.cpp")
+LIB = os.path.join(ROOT, "tests", "emu", "libemu_features.so")
+CSRC = os.path.join(ROOT, "multimodal-sentiment-analyzer_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("msa_features_body.cuh", "msa_fft.cuh", "msa_tables.hpp", "msa_hd.h")]
+    if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread", "-I", CSRC, SRC, "-o", LIB])
+    return ctypes.CDLL(LIB)
+
+
+def run(lib, x, nranks=4, nwarps=4, flags=1, parts=7, emo=None):
+    x = np.ascontiguousarray(x)
+    B, T = x.shape
+    feat = np.zeros((B, 31), np.float32)
+    det = np.zeros((B, 96), np.float32)
+    dbg = np.zeros((B, T // 200 + 1, 13), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.emu_features(p(x), int(x.dtype == np.int16), B, T, nranks, nwarps,
+                          None if emo is None else p(np.ascontiguousarray(emo)), p(feat), p(det), p(dbg), flags, parts)
+    assert rc == 0
+    return feat, det, dbg
+
+
+def check_against_oracle(det, feat, x, emo=None, rel=1e-3, floor=1e-5):
+    """Tolerances of SURVEY.md section 8(d): rel 1e-3 (abs floor), pitch abs 1e-6, exact flags."""
+    raw = fx.raw_features(x, emo)
+    q = fx.quality4(x)
+    got = det[:27].astype(np.float64)
+    assert abs(got[8]) <= 1e-6 and abs(raw[8]) <= 1e-6                      # "pitch" is rounding noise
+    assert np.isnan(got[9]) and np.isnan(raw[9])                            # mono intensity is NaN
+    for sl in (slice(0, 8), slice(10, 23), slice(24, 26)):
+        a, b = got[sl], raw[sl]
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        ok = ~np.isnan(b)
+        assert np.all(np.abs(a[ok] - b[ok]) <= rel * np.abs(b[ok]) + floor), (a, b)
+    assert got[23] == raw[23]                                               # speech_rate exact
+    assert np.float32(got[26]) == np.float32(raw[26])                       # L/16000 exact
+    gq = det[27:31].astype(np.float64)
+    assert np.array_equal(np.isnan(gq), np.isnan(q))
+    ok = ~np.isnan(q)
+    assert np.all(np.abs(gq[ok] - q[ok]) <= rel * np.abs(q[ok]) + floor), (gq, q)
+    row = fx.audio_row31(x, emo)
+    assert np.all(np.abs(feat - row) <= rel * np.abs(row) + floor)
+
+
+@pytest.mark.parametrize("nranks,nwarps", [(1, 8), (2, 4), (4, 8), (8, 2)])
+def test_seeded_segment_all_cluster_sizes(emu, nranks, nwarps):
+    x = synth.pcm_to_f32(synth.segment_pcm(1234))
+    feat, det, dbg = run(emu, x[None], nranks, nwarps)
+    check_against_oracle(det[0], feat[0], x)
+    ref = fx.mfcc(x.astype(np.float64)).T
+    assert np.abs(dbg[0] - ref).max() < 1e-3                                # MFCC matrix itself (values up to ~170)
+    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6                          # STFT->ISTFT residual: std, max
+
+
+def test_int16_ingest_matches_f32(emu):
+    pcm = synth.segments_pcm(2000, 2)
+    f16, d16, _ = run(emu, pcm, 4, 4)
+    f32, d32, _ = run(emu, synth.pcm_to_f32(pcm), 4, 4)
+    assert np.array_equal(f16, f32)
+    assert np.array_equal(d16[:, :31], d32[:, :31], equal_nan=True)
+
+
+def test_emotion_embedding_and_finite_ln(emu):
+    x = synth.pcm_to_f32(synth.segment_pcm(1240))
+    emo = synth.emotion_probs(5, 1)
+    feat, det, _ = run(emu, x[None], 4, 4, flags=0, emo=emo)                # flags=0: intensity 0 instead of NaN
+    raw = fx.raw_features(x, emo[0])
+    raw[9] = 0.0
+    ln = fx.ln31(raw)
+    assert np.allclose(det[0, 32:63], ln, rtol=1e-3, atol=1e-5)
+    row = fx.audio_row31(x, emo[0], finite_intensity=True)
+    assert np.allclose(feat[0], row, rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["white_0p1", "zeros", "noise_1e-4", "tone_220", "half_silence",
+                                  "short_8000", "odd_12345", "short_1700", "short_500", "long_10s"])
+def test_adversarial(emu, name):
+    x = synth.adversarial_cases()[name]
+    T = x.size
+    nranks = 8 if T > 100000 else (4 if T > 20000 else (2 if T > 4000 else 1))
+    feat, det, _ = run(emu, x[None], nranks, 4)
+    # near-silent input: mel bins sit at / next to the 1e-10 floor, where fp32 FFT noise decides the dB value
+    rel, floor = (1e-3, 1e-5) if name not in ("noise_1e-4", "zeros") else (2e-3, 2e-4)
+    check_against_oracle(det[0], feat[0], x, rel=rel, floor=floor)
+
+
+def test_batch_rows_are_independent(emu):
+    pcm = synth.segments_pcm(3000, 3)
+    fb, db, _ = run(emu, pcm, 4, 2)
+    for i in range(3):
+        f1, d1, _ = run(emu, pcm[i:i + 1], 4, 2)
+        assert np.array_equal(fb[i], f1[0])

@@ -1,0 +1,172 @@
+"""GPU parity of the fused feature kernel (through the C ABI) against the golden vectors of the
+reference, the numpy oracle, and size-independent properties at the benchmark size.
+
+Tolerances: timbre / rhythm[0:2] / quality floats rel 1e-3 (abs floor 1e-5);
+rhythm[2] and speech_rate exact; "pitch" |v| <= 1e-6 absolute (the reference value is rounding
+noise ~1e-9); intensity NaN for mono; NaN pattern of the LayerNorm row identical.
+"""
+import os
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import features_np as fx
+from oracle import synth
+from tests.gpu_util import close, need_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ana():
+    need_gpu()
+    import msa_b200
+    return msa_b200.AudioAnalyzer(device="cuda:0")
+
+
+def _detail(ana, x, cluster=0, parts=7, emo=None, flags=None):
+    from msa_b200 import _lib
+    w = torch.from_numpy(np.ascontiguousarray(x)).to(ana.device)
+    B, T = w.shape
+    feat = torch.empty(B, 31, device=ana.device)
+    det = torch.empty(B, 96, device=ana.device)
+    mf = torch.empty(B, T // 200 + 1, 13, device=ana.device)
+    e = None if emo is None else torch.from_numpy(emo).to(ana.device)
+    fn = ana._lib.msa_features_s16 if w.dtype == torch.int16 else ana._lib.msa_features_f32
+    rc = fn(_lib.ptr(w), B, T, _lib.ptr(e), _lib.ptr(feat), _lib.ptr(det), _lib.ptr(mf), ana._flags() if flags is None else flags,
+            parts, cluster, _lib.current_stream_ptr(ana.device))
+    assert rc == 0, _lib.strerror(rc)
+    torch.cuda.synchronize()
+    return feat.cpu().numpy(), det.cpu().numpy(), mf.cpu().numpy()
+
+
+def _check_vs_reference_row(det, ref_timbre, ref_rhythm, ref_q, ref_rate, what):
+    assert abs(det[8]) <= 1e-6, what
+    assert np.isnan(det[9]), what
+    close(det[10:23], ref_timbre, what=what + " timbre")
+    close(det[24:26], ref_rhythm[:2], what=what + " rhythm")
+    assert np.float32(det[26]) == np.float32(ref_rhythm[2]), what
+    assert det[23] == ref_rate, what
+    close(det[27:31], ref_q, what=what + " quality")
+
+
+def test_golden_seeded_segments(ana, golden_features):
+    g = golden_features
+    seeds = [int(s) for s in g["seeds"]]
+    x = np.stack([synth.pcm_to_f32(synth.segment_pcm(s)) for s in seeds])
+    feat, det, _ = _detail(ana, x)
+    for i in range(len(seeds)):
+        _check_vs_reference_row(det[i], g["seg_timbre"][i], g["seg_rhythm"][i], g["seg_quality4"][i], g["seg_speech_rate"][i][0],
+                                f"seed {seeds[i]}")
+        assert np.all(feat[i, :27] == 0.0)                       # NaN row -> nan_to_num -> zeros (strict reference)
+        close(feat[i, 27:], g["seg_quality4"][i])
+    for i in range(4):                                          # analyze() rows: identical NaN pattern
+        row = np.concatenate([det[i, 32:59], det[i, 27:31]])
+        close(row, g["analyze_rows"][i], what="analyze row")
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_cluster_sizes_agree_with_oracle(ana, cluster):
+    x = synth.pcm_to_f32(synth.segment_pcm(1234))[None]
+    _, det, mf = _detail(ana, x, cluster=cluster)
+    raw, q = fx.raw_features(x[0]), fx.quality4(x[0])
+    close(det[0, 10:23], raw[10:23], what="timbre")
+    close(det[0, 24:27], raw[24:27], what="rhythm")
+    close(det[0, 27:31], q, what="quality")
+    assert np.abs(mf[0] - fx.mfcc(x[0].astype(np.float64)).T).max() < 2e-3      # MFCC values reach ~170
+    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6               # STFT -> ISTFT residual: std, max
+    assert det[0, 72] == 80000                                   # every sample reconstructed exactly once
+
+
+def test_int16_ingest_equals_f32(ana):
+    pcm = synth.segments_pcm(2000, 3)
+    f16, d16, _ = _detail(ana, pcm)
+    f32, d32, _ = _detail(ana, synth.pcm_to_f32(pcm))
+    assert np.array_equal(f16, f32)
+    assert np.array_equal(d16[:, :63], d32[:, :63], equal_nan=True)
+
+
+def test_finite_layernorm_and_emotion_embedding(ana, golden_features):
+    g = golden_features
+    seeds = [int(s) for s in g["seeds"][:4]]
+    x = np.stack([synth.pcm_to_f32(synth.segment_pcm(s)) for s in seeds])
+    feat, det, _ = _detail(ana, x, flags=2)                     # not strict: intensity 0 -> finite LayerNorm row
+    for i in range(4):
+        close(det[i, 32:63], g["ln31_finite"][i], rel=1e-3, floor=2e-5, what="ln31")
+    emo = synth.emotion_probs(5, 4)
+    feat, det, _ = _detail(ana, x, emo=emo, flags=2)
+    for i in range(4):
+        close(feat[i], fx.audio_row31(x[i], emo[i], finite_intensity=True), rel=1e-3, floor=2e-5, what="row with emotion")
+
+
+@pytest.mark.parametrize("name", list(synth.adversarial_cases().keys()))
+def test_adversarial_vs_golden(ana, golden_features, name):
+    g = golden_features
+    x = synth.adversarial_cases()[name]
+    if x.size <= 256:
+        pytest.skip("covered by the shim test")
+    _, det, _ = _detail(ana, x[None])
+    d = det[0]
+    ref = {k: g[f"adv_{name}_{k}"] for k in ("pitch", "timbre", "speech_rate", "rhythm", "quality4")}
+    rel, floor = (1e-3, 1e-5) if name not in ("noise_1e-4", "zeros") else (2e-3, 2e-4)
+    assert abs(d[8]) <= 1e-6
+    close(d[10:23], ref["timbre"], rel, floor, what="timbre")
+    close(d[24:26], ref["rhythm"][:2], rel, 1e-9 + floor * 0, what="rhythm")
+    assert np.float32(d[26]) == ref["rhythm"][2]
+    assert d[23] == ref["speech_rate"][0]
+    close(d[27:31], ref["quality4"], rel, floor, what="quality")
+
+
+def test_reference_method_shims(ana, golden_features, tmp_path):
+    g = golden_features
+    x = synth.pcm_to_f32(synth.segment_pcm(1234))
+    w = torch.from_numpy(x)[None].to(ana.device)
+    assert ana._analyze_pitch(w).shape == (1, 1) and abs(ana._analyze_pitch(w).item()) <= 1e-6
+    assert torch.isnan(ana._analyze_intensity(w)).all()
+    close(ana._analyze_timbre(w).cpu().numpy()[0], g["seg_timbre"][0], what="timbre")
+    assert ana._analyze_speech_rate(w).item() == 1.0
+    r = ana._analyze_rhythm(w).cpu().numpy()[0]
+    close(r[:2], g["seg_rhythm"][0][:2], what="rhythm")
+    q = [ana._calculate_audio_quality(w), ana._calculate_signal_noise_ratio(w), ana._calculate_clarity(w), ana._calculate_consistency(w)]
+    close(q, g["seg_quality4"][0], what="quality")
+    assert torch.allclose(ana._analyze_emotion(w), torch.full((1, 8), 0.125, device=ana.device))
+    # reference error convention: malformed input -> the method's default, never an exception
+    assert torch.equal(ana._analyze_timbre(w[0]), torch.zeros(1, 13, device=ana.device))
+    assert torch.equal(ana._analyze_rhythm(w[:, :300]), torch.zeros(1, 3, device=ana.device))
+    assert ana._calculate_consistency(w[:, :1000]) == 0.0
+    assert torch.equal(ana._analyze_pitch(w[:, :200]), torch.zeros(1, 1, device=ana.device))
+    # analyze(path, speaker) through a real PCM wav file
+    p = os.path.join(tmp_path, "seg.wav")
+    with wave.open(p, "wb") as wf:
+        wf.setnchannels(1); wf.setsampwidth(2); wf.setframerate(16000)
+        wf.writeframes(synth.segment_pcm(1234).tobytes())
+    a = ana.analyze(p, "spk7")
+    assert a.speaker_id == "spk7" and a["timbre"].shape == (1, 13) and a.get("rhythm").shape == (1, 3)
+    row = torch.cat([a.emotion_probs, a.pitch, a.intensity, a.timbre, a.speech_rate, a.rhythm], dim=1).cpu().numpy()[0]
+    close(np.concatenate([row, [a.audio_quality, a.signal_noise_ratio, a.clarity, a.consistency]]), g["analyze_rows"][0], what="analyze")
+    assert isinstance(a.to_dict(), dict)
+    d = ana.analyze(os.path.join(tmp_path, "missing.wav"), "x")           # failure -> default analysis
+    assert d.audio_quality == 0.0 and torch.equal(d.emotion_probs, torch.full((1, 8), 0.125, device=ana.device))
+
+
+def test_full_size_batch_properties(ana):
+    """BASELINE config 2 (1024 x 5 s): rows are independent and deterministic, flags exact."""
+    pcm = torch.from_numpy(synth.fast_segments_pcm(7, 1024)).to(ana.device)
+    f1, d1 = ana.analyze_batch(pcm, return_detail=True)
+    f2, d2 = ana.analyze_batch(pcm, return_detail=True)
+    torch.cuda.synchronize()
+    assert torch.equal(f1, f2) and torch.equal(d1[:, :63].nan_to_num(7.0), d2[:, :63].nan_to_num(7.0))     # deterministic
+    idx = [0, 511, 1023]
+    fs, ds = ana.analyze_batch(pcm[idx].contiguous(), return_detail=True)
+    assert torch.equal(fs, f1[idx])                                                  # batch == loop of [1,T] calls
+    d = d1.cpu().numpy()
+    assert np.all(np.abs(d[:, 8]) <= 1e-6) and np.all(np.isnan(d[:, 9])) and np.all(d[:, 23] == 1.0)
+    assert np.all(d[:, 26] == np.float32(498 / 16000)) and np.all(d[:, 72] == 80000)
+    assert np.all(d[:, 66] < 1e-6)                                                   # perfect reconstruction everywhere
+    assert np.all((d[:, 27:31] >= 0) & (d[:, 27:31] <= 1))
+    for i in idx:                                                                    # spot-check against the oracle
+        x = synth.pcm_to_f32(pcm[i].cpu().numpy())
+        close(d[i, 10:23], fx.timbre(x), what="timbre")
+        close(d[i, 27:31], fx.quality4(x), what="quality")

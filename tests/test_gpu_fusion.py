@@ -1,0 +1,172 @@
+"""GPU parity of AdvancedFusionModel.forward (through the C ABI) against the golden logits of the
+reference and the numpy oracle.
+
+Bar: logits abs 1e-3, argmax equal on >= 99.9 % of rows, reference dict
+semantics (keys, pass-through objects, fallbacks) identical.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_np as fu
+from oracle import synth
+from tests.gpu_util import need_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(trained_like, impl):
+    import msa_b200
+    from msa_b200 import _lib
+    assert _lib.lib().msa_fusion_set_impl(impl) == 0
+    sd = synth.fusion_state(4321, trained_like=trained_like)
+    m = msa_b200.AdvancedFusionModel(device="cuda:0")
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    return m, sd
+
+
+def _inputs(n, dev):
+    f, a, t = synth.face_rows(1, n), synth.audio_rows(2, n), synth.text_rows(3, n)
+    return (f, a, t), tuple(torch.from_numpy(v).to(dev) for v in (f, a, t))
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("tag,trained", [("init", False), ("trained", True)])
+def test_golden_logits(golden_fusion, impl, tag, trained):
+    dev = need_gpu()
+    g = golden_fusion
+    m, _ = _model(trained, impl)
+    n = g[f"{tag}_fused3"].shape[0]
+    _, (f, a, t) = _inputs(n, dev)
+    out3 = m(f, a, t)
+    out2 = m(f, a, None)
+    torch.cuda.synchronize()
+    assert sorted(out3.keys()) == list(g[f"{tag}_keys3"]) and sorted(out2.keys()) == list(g[f"{tag}_keys2"])
+    assert out3["face"] is f and out3["audio"] is a and out3["text"] is t          # returned by reference
+    l3, l2 = out3["fused"].cpu().numpy(), out2["fused"].cpu().numpy()
+    assert np.abs(l3 - g[f"{tag}_fused3"]).max() < 1e-3, np.abs(l3 - g[f"{tag}_fused3"]).max()
+    assert np.abs(l2 - g[f"{tag}_fused2"]).max() < 1e-3, np.abs(l2 - g[f"{tag}_fused2"]).max()
+    assert np.array_equal(l3.argmax(1), g[f"{tag}_fused3"].argmax(1))
+    assert np.array_equal(l2.argmax(1), g[f"{tag}_fused2"].argmax(1))
+
+
+def test_dispatch_and_fallbacks(golden_fusion):
+    dev = need_gpu()
+    g = golden_fusion
+    m, _ = _model(False, 0)
+    _, (f, a, t) = _inputs(8, dev)
+    assert sorted(m(f, None, t).keys()) == list(g["init_keys_face_text"])
+    assert sorted(m(None, a, t).keys()) == list(g["init_keys_audio_text"])
+    r = m(None, a, None)
+    assert sorted(r.keys()) == list(g["init_keys_audio_only"]) and r["audio"] is a
+    assert sorted(m(f[:, :20], a, t).keys()) == list(g["init_keys_bad_dim"])
+    w = m.get_weights()
+    assert np.allclose([w["audio"], w["text"], w["face"]], g["init_weights"], rtol=1e-6)
+    with pytest.raises(ValueError):
+        m(None, None, None)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_argmax_agreement_and_ragged_batches(impl):
+    """4096 + 77 rows (not a multiple of the 128-row tile) against the fp64 oracle."""
+    dev = need_gpu()
+    m, sd = _model(True, impl)
+    n = 4096 + 77
+    (f, a, t), (fd, ad, td) = _inputs(n, dev)
+    logits, amax = m.fused_with_argmax(fd, ad, td)
+    torch.cuda.synchronize()
+    ref = fu.fuse_all(sd, f, a, t)
+    l = logits.cpu().numpy()
+    assert np.abs(l - ref).max() < 1e-3, np.abs(l - ref).max()
+    agree = (l.argmax(1) == ref.argmax(1)).mean()
+    assert agree >= 0.999, agree
+    assert np.array_equal(amax.cpu().numpy(), l.argmax(1))
+    l1, _ = m.fused_with_argmax(fd[:1], ad[:1], td[:1])                              # B = 1 (streaming)
+    assert np.abs(l1.cpu().numpy() - ref[:1]).max() < 1e-3
+    l2, _ = m.fused_with_argmax(fd[:300], ad[:300], None)
+    assert np.abs(l2.cpu().numpy() - fu.fuse_face_audio(sd, f[:300], a[:300])).max() < 1e-3
+
+
+def test_tcgen05_matches_simt_on_device():
+    dev = need_gpu()
+    n = 2048
+    _, (f, a, t) = _inputs(n, dev)
+    m1, _ = _model(True, 1)
+    ls, _ = m1.fused_with_argmax(f, a, t)
+    m0, _ = _model(True, 0)
+    lt, _ = m0.fused_with_argmax(f, a, t)
+    torch.cuda.synchronize()
+    assert (ls - lt).abs().max().item() < 5e-4
+    assert (ls.argmax(1) == lt.argmax(1)).float().mean().item() >= 0.999
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    dev = need_gpu()
+    m, _ = _model(True, 0)
+    _, (f, a, t) = _inputs(64, dev)
+    before = m(f, a, t)["fused"].clone()
+    p = str(tmp_path / "ck" / "fusion.pt")
+    m.save(p)
+    import msa_b200
+    m2 = msa_b200.AdvancedFusionModel.load(p, device="cuda:0")
+    assert torch.equal(m2(f, a, t)["fused"], before)
+    w1, w2 = m.get_weights(), m2.get_weights()
+    assert w1 != w2 and abs(sum(w2.values()) - 1.0) < 1e-6           # load() stores the SOFTMAXED scalars (reference quirk)
+    m3 = msa_b200.FusionModel.load(str(tmp_path / "new" / "fresh.pt"), device="cuda:0")   # missing file -> fresh model, saved
+    assert (tmp_path / "new" / "fresh.pt").exists() and "fused" in m3(f, a, t)
+    m3.fusion[8].bias.data.add_(1.0)                                  # parameter edits are picked up (lazy repack)
+    assert (m3(f, a, t)["fused"] - 1.0).abs().max() < 1e3
+
+
+def test_pipeline_and_aggregation():
+    dev = need_gpu()
+    import msa_b200
+    ana = msa_b200.AudioAnalyzer(device="cuda:0")
+    m, sd = _model(True, 0)
+    n = 24
+    pcm = torch.from_numpy(synth.segments_pcm(1234, n)).to(dev)
+    (f, a, t), (fd, ad, td) = _inputs(n, dev)
+    pipe = msa_b200.SegmentPipeline(ana, m)
+    rows = pipe.run(pcm, fd, td, first_id=100)
+    from msa_b200.pipeline import unpack_rows
+    r = unpack_rows(rows)
+    torch.cuda.synchronize()
+    assert r["segment_id"].tolist() == list(range(100, 100 + n))
+    audio_row = r["audio_row"].cpu().numpy()
+    ref = fu.fuse_all(sd, f, audio_row, t)
+    assert np.abs(r["logits"].cpu().numpy() - ref).max() < 1e-3
+    assert np.array_equal(r["argmax"].cpu().numpy(), ref.argmax(1))
+    # speaker aggregation vs the reference's python (offline_processor.py:287-298)
+    rng = np.random.default_rng(0)
+    labels = rng.integers(0, 3, 500).astype(np.int32)
+    spk = rng.integers(0, 4, 500).astype(np.int32)
+    out = msa_b200.aggregate_speakers(torch.from_numpy(labels).to(dev), torch.from_numpy(spk).to(dev), 5)
+    for p in range(5):
+        em = [int(e) for e, s in zip(labels, spk) if s == p]
+        hist = np.bincount(em, minlength=7) if em else np.zeros(7, int)
+        assert out["hist"][p].tolist() == hist.tolist()
+        assert out["dominant"][p].item() == (max(sorted(set(em)), key=em.count) if em else -1)
+        idx = [i for i, s in enumerate(spk) if s == p]
+        starts = {idx[i] for i in range(len(em) - 2) if em[i] == em[i + 1] == em[i + 2]}
+        got = {i for i in idx if out["run3"][i].item() == 1}
+        assert got == starts
+
+
+def test_streaming_window_equals_offline():
+    dev = need_gpu()
+    import msa_b200
+    ana = msa_b200.AudioAnalyzer(device="cuda:0")
+    m, _ = _model(True, 0)
+    pcm = synth.segment_pcm(77, 80000 + 3 * 8000)
+    face = torch.from_numpy(synth.face_rows(9, 1)).to(dev)
+    sw = msa_b200.StreamingWindow(ana, m)
+    outs = []
+    for i in range(13):
+        o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), face)
+        outs.append(o)
+    assert all(o is None for o in outs[:9]) and all(o is not None for o in outs[9:])
+    for j, o in enumerate(outs[9:]):
+        seg = torch.from_numpy(pcm[j * 8000: j * 8000 + 80000].copy())[None].to(dev)
+        row = ana.analyze_batch(seg)
+        logits, _ = m.fused_with_argmax(face, row, None)
+        assert torch.equal(o["audio_row"], row[0]) and torch.equal(o["fused_emotion"], logits[0])

@@ -1,0 +1,88 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/msa_b200.h
+declares, capacity queries work without a device, host-side sharding / row packing logic, the
+reference-compatible state_dict layout, and the loud failure of compute calls without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import msa_b200
+    return msa_b200
+
+
+def test_header_symbols_are_exported(built):
+    from msa_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "msa_b200.h")).read()
+    declared = set(re.findall(r"\b(msa_[a-z0-9_]+)\s*\(", hdr))
+    l = _lib.lib()
+    for name in declared:
+        assert hasattr(l, name), f"{name} declared in include/msa_b200.h but not exported"
+    assert declared == set(_lib.exported_symbols())
+
+
+def test_capacity_queries_without_device(built):
+    from msa_b200 import _lib
+    l = _lib.lib()
+    assert l.msa_version() >= 100
+    assert l.msa_features_cluster_size(80000) == 4
+    assert l.msa_features_cluster_size(8000) == 1
+    assert l.msa_features_cluster_size(160000) == 8
+    assert l.msa_features_cluster_size(320000) == 16
+    assert l.msa_features_cluster_size(2_000_000) == 0                    # unsupported: too long for one cluster
+    assert 0 < l.msa_features_smem_bytes(80000, 4) <= 232448
+    assert l.msa_fusion_num_tensors() == 42
+    assert l.msa_strerror(0) == b"ok" and b"too long" in l.msa_strerror(-2)
+    assert l.msa_fusion_workspace_bytes(1024) > 0 and l.msa_fusion_packed_bytes() > 4 * 5_600_000
+
+
+def test_state_dict_matches_reference_layout(built):
+    """45 tensors, 5,604,508 parameters, reference key names."""
+    from msa_b200 import _lib
+    from oracle import synth
+    m = built.AdvancedFusionModel(device="cpu")
+    sd = m.state_dict()
+    assert len(sd) == 45 and sum(v.numel() for v in sd.values()) == 5_604_508
+    assert set(sd.keys()) == set(synth.fusion_state(0).keys())
+    l = _lib.lib()
+    names = [l.msa_fusion_tensor_name(i).decode() for i in range(l.msa_fusion_num_tensors())]
+    assert set(names) == set(sd.keys()) - {"audio_weight", "text_weight", "face_weight"}
+    for i, n in enumerate(names):
+        assert l.msa_fusion_tensor_numel(i) == sd[n].numel()
+    w = m.get_weights()                                                    # 0.3 / 0.3 / 0.4 -> softmax
+    assert abs(w["audio"] - 0.3220) < 1e-3 and abs(w["face"] - 0.3559) < 1e-3
+    # single-modality pass-through and the always-failing pairs need no device
+    a = torch.randn(2, 31)
+    assert m(None, a, None)["audio"] is a
+    assert list(m(None, a, torch.randn(2, 783)).keys()) == ["audio"]
+
+
+def test_no_cpu_fallback(built):
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from msa_b200 import _lib
+    with pytest.raises(_lib.MsaError):
+        built.AudioAnalyzer(device="cuda")
+    m = built.AdvancedFusionModel(device="cpu")
+    with pytest.raises(_lib.MsaError):
+        m(torch.randn(2, 27), torch.randn(2, 31), torch.randn(2, 783))
+
+
+def test_shard_ranges_and_row_packing(built):
+    from msa_b200.pipeline import pack_rows, shard_range, unpack_rows
+    for n, w in ((720, 8), (1024, 3), (5, 8), (0, 2)):
+        r = [shard_range(n, w, k) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+        sizes = [e - b for b, e in r]
+        assert max(sizes) - min(sizes) <= 1
+    rows = pack_rows(torch.randn(5, 31), torch.randn(5, 7), torch.tensor([6, 0, 3, 2, 1]), 1 << 20)
+    u = unpack_rows(rows)
+    assert u["argmax"].tolist() == [6, 0, 3, 2, 1] and u["segment_id"].tolist() == list(range(1 << 20, (1 << 20) + 5))
