@@ -119,3 +119,24 @@ def test_fusion_against_reference(golden_fusion):
         w = fu.get_weights(sd)
         assert np.allclose([w["audio"], w["text"], w["face"]], g[f"{tag}_weights"], rtol=1e-6)
     out3["face"] is face
+
+
+def test_torch_port_matches_reference(golden_features, golden_fusion):
+    """The timed CPU baseline (oracle/torch_port.py) reproduces the reference's numbers."""
+    import torch
+    from oracle import torch_port as tp
+    g = golden_features
+    ana = tp.PortedAnalyzer()
+    for i, seed in enumerate(g["seeds"][:3]):
+        w = torch.from_numpy(synth.pcm_to_f32(synth.segment_pcm(int(seed))))[None, :]
+        row = ana.audio_row(w).numpy()[0]
+        assert np.all(row[:27] == 0.0)
+        _close(row[27:], g["seg_quality4"][i])
+        _close(ana.timbre(w).numpy()[0], g["seg_timbre"][i], rel=1e-6, floor=1e-6)
+        _close(ana.rhythm(w).numpy()[0], g["seg_rhythm"][i], rel=1e-6, floor=1e-7)
+    gf = golden_fusion
+    sd = tp.build_fusion(synth.fusion_state(int(gf["weight_seed"]), trained_like=True))
+    n = gf["trained_fused3"].shape[0]
+    f, a, t = (torch.from_numpy(v) for v in (synth.face_rows(1, n), synth.audio_rows(2, n), synth.text_rows(3, n)))
+    assert np.abs(tp.fusion_forward(sd, f, a, t).numpy() - gf["trained_fused3"]).max() < 1e-5
+    assert np.abs(tp.fusion_forward(sd, f, a, None).numpy() - gf["trained_fused2"]).max() < 1e-5
