@@ -67,9 +67,9 @@ def test_golden_seeded_segments(ana, golden_features):
         close(row, g["analyze_rows"][i], what="analyze row")
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
-def test_cluster_sizes_agree_with_oracle(ana, cluster):
-    x = synth.pcm_to_f32(synth.segment_pcm(1234))[None]
+@pytest.mark.parametrize("cluster,T", [(4, 80000), (8, 80000), (16, 80000), (1, 16000), (2, 16000), (2, 30001)])
+def test_cluster_sizes_agree_with_oracle(ana, cluster, T):
+    x = synth.pcm_to_f32(synth.segment_pcm(1234, T))[None]
     _, det, mf = _detail(ana, x, cluster=cluster)
     raw, q = fx.raw_features(x[0]), fx.quality4(x[0])
     close(det[0, 10:23], raw[10:23], what="timbre")
@@ -77,7 +77,10 @@ def test_cluster_sizes_agree_with_oracle(ana, cluster):
     close(det[0, 27:31], q, what="quality")
     assert np.abs(mf[0] - fx.mfcc(x[0].astype(np.float64)).T).max() < 2e-3      # MFCC values reach ~170
     assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6               # STFT -> ISTFT residual: std, max
-    assert det[0, 72] == 80000                                   # every sample reconstructed exactly once
+    assert det[0, 72] == T                                       # every sample reconstructed exactly once
+    from msa_b200 import _lib
+    assert ana._lib.msa_features_f32(_lib.ptr(torch.zeros(1, 80000, device=ana.device)), 1, 80000, None,
+                                     _lib.ptr(torch.zeros(1, 31, device=ana.device)), None, None, 1, 7, 1, None) == -2   # too long for 1 CTA
 
 
 def test_int16_ingest_equals_f32(ana):
