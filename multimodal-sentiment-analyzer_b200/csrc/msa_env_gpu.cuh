@@ -12,6 +12,7 @@ namespace cg = cooperative_groups;
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 struct GpuEnv {
+  static constexpr int kLanes = 32;
   int tid, nthreads, lane, nlanes, warp, nwarps, rank, nranks, cluster_id;
 
   __device__ __forceinline__ void sync() { __syncthreads(); }

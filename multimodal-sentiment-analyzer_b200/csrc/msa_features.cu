@@ -1,6 +1,7 @@
 // Launch side of the fused audio-feature kernel (see msa_features_body.cuh for the algorithm).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "msa_api_internal.h"
@@ -8,8 +9,8 @@
 
 namespace msa {
 
-template <class InT>
-__global__ void __launch_bounds__(kFeatThreads, 1) features_kernel(const FeatParams P) {
+template <class InT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) features_kernel(const FeatParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   GpuEnv env;
@@ -53,13 +54,27 @@ static int slice_len_for(int T, int c) {
   return ((L + kAtom - 1) / kAtom) * kAtom;
 }
 
+// Tuning knobs (read once): MSA_FEAT_THREADS = 256 | 512 threads per CTA, MSA_FEAT_SLICE = preferred
+// samples per CTA (the cluster grows until a slice is at most this long and fits shared memory).
+static int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return (e && *e) ? std::atoi(e) : dflt;
+}
+int feat_threads() {
+  static const int t = (env_int("MSA_FEAT_THREADS", kFeatThreads) == 256) ? 256 : 512;
+  return t;
+}
+static int feat_slice_pref() {
+  static const int s = env_int("MSA_FEAT_SLICE", kFeatSlicePref);
+  return s;
+}
+
 int features_cluster_size(int T) {
   if (T < 1) return 0;
-  const int nwarps = kFeatThreads / 32;
-  // prefer slices of <= 20000 samples (5 s -> 4 CTAs); grow the cluster while a slice does not fit
+  const int nwarps = feat_threads() / 32;
   for (int c = 1; c <= 16; c *= 2) {
     const int L = slice_len_for(T, c);
-    if (L <= 20000 && feat_layout(L, nwarps).total <= kMaxSmem) return c;
+    if (L <= feat_slice_pref() && feat_layout(L, nwarps).total <= kMaxSmem) return c;
   }
   for (int c = 1; c <= 16; c *= 2)
     if (feat_layout(slice_len_for(T, c), nwarps).total <= kMaxSmem) return c;
@@ -68,7 +83,7 @@ int features_cluster_size(int T) {
 
 int features_smem_bytes(int T, int c) {
   if (T < 1 || c < 1) return 0;
-  return feat_layout(slice_len_for(T, c), kFeatThreads / 32).total;
+  return feat_layout(slice_len_for(T, c), feat_threads() / 32).total;
 }
 
 template <class InT>
@@ -100,10 +115,11 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.tab = tab;
   P.flags = flags;
   P.parts = parts;
-  const FeatLayout lay = feat_layout(P.slice_len, kFeatThreads / 32);
+  const int threads = feat_threads();
+  const FeatLayout lay = feat_layout(P.slice_len, threads / 32);
   if (lay.total > kMaxSmem) return MSA_ERR_UNSUPPORTED_LENGTH;
 
-  auto kern = features_kernel<InT>;
+  auto kern = (threads == 256) ? features_kernel<InT, 256> : features_kernel<InT, 512>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
   if (e != cudaSuccess) return (int)e;
   if (c > 8) {
@@ -112,7 +128,7 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)B * c, 1, 1);
-  cfg.blockDim = dim3(kFeatThreads, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
   cfg.dynamicSmemBytes = lay.total;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -14,10 +14,14 @@
 //
 // Work split: the segment's samples [0,T) are cut into `nranks` contiguous slices; CTA `rank`
 // stages its slice (+512-sample halos) in shared memory ONCE (the only HBM read of the
-// waveform) and computes, from shared memory, every MFCC frame whose centre, every pitch hop
-// whose start and every 80-sample energy atom that falls in its slice.  The whole-segment
-// dependencies (top_db max, z-score moments, frame-energy statistics) are exchanged through
-// distributed shared memory; rank 0 assembles the 31-float row.
+// waveform) and computes, from shared memory, every MFCC frame whose centre, every output
+// sample of the STFT->ISTFT round trip and every 80-sample energy atom that falls in its slice.
+// The whole-segment dependencies (top_db max, z-score moments, frame-energy statistics) are
+// exchanged through distributed shared memory; rank 0 assembles the 31-float row.
+//
+// FFTs: one warp per transform, in place in shared memory, two real frames packed into one
+// complex transform (msa_fft.cuh).  Warps run independently; only the overlap-add of the ISTFT
+// needs block barriers (once per batch of 2*nwarps frames).
 //
 // This file is compiled by nvcc (GpuEnv, msa_features.cu) and by g++ (CpuEnv, tests/emu)
 // so the index logic can be exercised without a GPU.  It must only use the Env primitives.
@@ -31,7 +35,6 @@ namespace msa {
 
 constexpr int kHalo = 512;
 constexpr int kDbStride = kMels + 1;       // 129: conflict-free row-per-thread reads in the DCT step
-constexpr int kPwStride = 208;             // 201 power bins padded
 constexpr int kDetailStride = 96;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
@@ -54,14 +57,15 @@ struct FeatParams {
 
 // tables staged in shared memory (the DCT matrix stays in global: warp-uniform reads through L1)
 struct SmemTables {
+  c32 tw512_s1[7 * 64];
+  c32 tw512_s2[7 * 8];
+  c32 tw400_s1[15 * 25];
+  c32 tw400_s2[4 * 5];
   float win400[kNfftM];
   float win512[kNfftP];
-  float tw400[2 * kNfftM];
-  float tw512[2 * kNfftP];
   float mel_w[kMelNnzMax];
-  uint16_t perm400[kNfftM];
+  uint16_t mel_pos[2 * kMelNnzMax];
   uint16_t mel_ptr[kMels + 2];
-  uint16_t mel_bin[kMelNnzMax];
 };
 
 struct Partials {
@@ -74,7 +78,7 @@ struct Partials {
 };
 
 struct FeatLayout {
-  int wave_off, zb_off, pw_off, dbs_off, mfcc_off, carry_off, atoms_off, tab_off, red_off, part_off, bar_off;
+  int wave_off, zb_off, dbs_off, mfcc_off, carry_off, atoms_off, tab_off, red_off, part_off, bar_off;
   int wave_cap, dbs_rows, total;
 };
 
@@ -93,7 +97,6 @@ FeatLayout feat_layout(int slice_len, int nwarps) {
   l.dbs_rows = slice_len / kHopM + 2;
   l.wave_off = take(l.wave_cap * 4);
   l.zb_off = take(nwarps * kPad512 * 8);
-  l.pw_off = take(nwarps * 2 * kPwStride * 4);
   l.dbs_off = take(l.dbs_rows * kDbStride * 4);
   l.mfcc_off = take(l.dbs_rows * kMfcc * 4);
   l.carry_off = take(2 * 3 * kHopP * 4);
@@ -118,6 +121,7 @@ MSA_FN double py_clip01(double v) {
 
 template <class Env, class InT>
 MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
+  constexpr int LANES = Env::kLanes;
   const int T = P.T, L = P.slice_len;
   const int seg = env.cluster_id, r = env.rank;
   const int t0 = (r * L < T) ? r * L : T;
@@ -129,7 +133,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   float* wave = reinterpret_cast<float*>(smem + lay.wave_off);
   c32* zb_all = reinterpret_cast<c32*>(smem + lay.zb_off);
-  float* pw_all = reinterpret_cast<float*>(smem + lay.pw_off);
   float* dbs = reinterpret_cast<float*>(smem + lay.dbs_off);
   float* mfcc = reinterpret_cast<float*>(smem + lay.mfcc_off);
   float* carry = reinterpret_cast<float*>(smem + lay.carry_off);
@@ -148,11 +151,21 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   // ---------------------------------------------------------------- stage tables + slice
   {
     const FeatureTables* g = P.tab;
-    for (int i = env.tid; i < kNfftM; i += env.nthreads) { tb->win400[i] = g->win400[i]; tb->perm400[i] = g->perm400[i]; }
+    const c32* s1 = reinterpret_cast<const c32*>(g->tw512_s1);
+    const c32* s2 = reinterpret_cast<const c32*>(g->tw512_s2);
+    const c32* m1 = reinterpret_cast<const c32*>(g->tw400_s1);
+    const c32* m2 = reinterpret_cast<const c32*>(g->tw400_s2);
+    for (int i = env.tid; i < 7 * 64; i += env.nthreads) tb->tw512_s1[i] = s1[i];
+    for (int i = env.tid; i < 7 * 8; i += env.nthreads) tb->tw512_s2[i] = s2[i];
+    for (int i = env.tid; i < 15 * 25; i += env.nthreads) tb->tw400_s1[i] = m1[i];
+    for (int i = env.tid; i < 4 * 5; i += env.nthreads) tb->tw400_s2[i] = m2[i];
+    for (int i = env.tid; i < kNfftM; i += env.nthreads) tb->win400[i] = g->win400[i];
     for (int i = env.tid; i < kNfftP; i += env.nthreads) tb->win512[i] = g->win512[i];
-    for (int i = env.tid; i < 2 * kNfftM; i += env.nthreads) tb->tw400[i] = g->tw400[i];
-    for (int i = env.tid; i < 2 * kNfftP; i += env.nthreads) tb->tw512[i] = g->tw512[i];
-    for (int i = env.tid; i < kMelNnzMax; i += env.nthreads) { tb->mel_w[i] = g->mel_w[i]; tb->mel_bin[i] = g->mel_bin[i]; }
+    for (int i = env.tid; i < kMelNnzMax; i += env.nthreads) {
+      tb->mel_w[i] = g->mel_w[i];
+      tb->mel_pos[2 * i] = g->mel_pos[2 * i];
+      tb->mel_pos[2 * i + 1] = g->mel_pos[2 * i + 1];
+    }
     for (int i = env.tid; i <= kMels; i += env.nthreads) tb->mel_ptr[i] = g->mel_ptr[i];
     for (int i = env.tid; i < 2 * 3 * kHopP; i += env.nthreads) carry[i] = 0.0f;
   }
@@ -172,7 +185,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     n_atoms_local = (a1 > a0) ? a1 - a0 : 0;
     for (int a = a0 + env.warp; a < a1; a += env.nwarps) {
       float s = 0.0f;
-      for (int i = env.lane; i < kAtom; i += env.nlanes) { float x = wave[a * kAtom + i - lo]; s = fmaf(x, x, s); }
+      for (int i = env.lane; i < kAtom; i += LANES) { float x = wave[a * kAtom + i - lo]; s = fmaf(x, x, s); }
       double sd = env.wsum((double)s);
       if (env.lane == 0) atoms[a - a0] = (float)sd;
     }
@@ -198,41 +211,43 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   float dbmax = -3.0e38f;
   {
     c32* zb = zb_all + env.warp * kPad512;
-    float* pw = pw_all + env.warp * 2 * kPwStride;
     const int npairs = (nfr + 1) / 2;
     for (int pp = env.warp; pp < npairs; pp += env.nwarps) {
       const int fa = fm_begin + 2 * pp;
       const bool hasb = (2 * pp + 1) < nfr;
       const int ca = fa * kHopM - kNfftM / 2, cb = ca + kHopM;
-      for (int n = env.lane; n < kNfftM; n += env.nlanes) {
-        const float w = tb->win400[n];
-        zb[n] = c32{w * W(ca + n), hasb ? w * W(cb + n) : 0.0f};
+      if (ca >= 0 && cb + kNfftM <= T) {                 // interior pair: no reflection (warp-uniform branch)
+        const float* wa = wave + (ca - lo);
+        for (int n = env.lane; n < kNfftM; n += LANES) {
+          const float w = tb->win400[n];
+          zb[n] = c32{w * wa[n], hasb ? w * wa[n + kHopM] : 0.0f};
+        }
+      } else {
+        for (int n = env.lane; n < kNfftM; n += LANES) {
+          const float w = tb->win400[n];
+          zb[n] = c32{w * W(ca + n), hasb ? w * W(cb + n) : 0.0f};
+        }
       }
       env.wsync();
-      fft_stage<kNfftM, 16, 400, false, PadNone>(zb, tb->tw400, env.lane, env.nlanes);
+      fft_stage<kNfftM, 16, 400, false, PadNone, LANES>(zb, tb->tw400_s1, env.lane);
       env.wsync();
-      fft_stage<kNfftM, 5, 25, false, PadNone>(zb, tb->tw400, env.lane, env.nlanes);
+      fft_stage<kNfftM, 5, 25, false, PadNone, LANES>(zb, tb->tw400_s2, env.lane);
       env.wsync();
-      fft_stage<kNfftM, 5, 5, false, PadNone>(zb, tb->tw400, env.lane, env.nlanes);
+      fft_stage<kNfftM, 5, 5, false, PadNone, LANES>(zb, nullptr, env.lane);
       env.wsync();
-      // untangle the two real spectra: A = (Z[k] + conj Z[N-k])/2, B = (Z[k] - conj Z[N-k])/(2i)
-      for (int k = env.lane; k < kBinsM; k += env.nlanes) {
-        const c32 zk = zb[tb->perm400[k]];
-        const c32 zn = zb[tb->perm400[(kNfftM - k) % kNfftM]];
-        const float sx = zk.x + zn.x, sy = zk.y - zn.y;
-        const float dx = zk.x - zn.x, dy = zk.y + zn.y;
-        pw[k] = 0.25f * (sx * sx + sy * sy);
-        pw[kPwStride + k] = 0.25f * (dx * dx + dy * dy);
-      }
-      env.wsync();
-      for (int m = env.lane; m < kMels; m += env.nlanes) {
+      // mel energies straight from the packed spectrum: with Z = FFT(a + i b),
+      //   |A_k|^2 = |Z_k + conj Z_{N-k}|^2 / 4,  |B_k|^2 = |Z_k - conj Z_{N-k}|^2 / 4
+      for (int m = env.lane; m < kMels; m += LANES) {
         const int p0 = tb->mel_ptr[m], p1 = tb->mel_ptr[m + 1];
         float ea = 0.0f, eb = 0.0f;
         for (int p = p0; p < p1; ++p) {
-          const float w = tb->mel_w[p];
-          const int bin = tb->mel_bin[p];
-          ea = fmaf(w, pw[bin], ea);
-          eb = fmaf(w, pw[kPwStride + bin], eb);
+          const c32 zk = zb[tb->mel_pos[2 * p]];
+          const c32 zn = zb[tb->mel_pos[2 * p + 1]];
+          const float w = 0.25f * tb->mel_w[p];
+          const float sx = zk.x + zn.x, sy = zk.y - zn.y;
+          const float dx = zk.x - zn.x, dy = zk.y + zn.y;
+          ea = fmaf(w, fmaf(sx, sx, sy * sy), ea);
+          eb = fmaf(w, fmaf(dx, dx, dy * dy), eb);
         }
         const float da = 10.0f * log10f(fmaxf(ea, 1e-10f));
         dbs[(2 * pp) * kDbStride + m] = da;
@@ -268,23 +283,31 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       if (fa <= pf_end) {
         const bool hasb = fa + 1 <= pf_end;
         const int sa = fa * kHopP - kNfftP / 2, sb = sa + kHopP;
-        for (int n = env.lane; n < kNfftP; n += env.nlanes) {
-          const float w = tb->win512[n];
-          zb[Pad8::at(n)] = c32{w * W(sa + n), hasb ? w * W(sb + n) : 0.0f};
+        if (sa >= 0 && sb + kNfftP <= T) {
+          const float* wa = wave + (sa - lo);
+          for (int n = env.lane; n < kNfftP; n += LANES) {
+            const float w = tb->win512[n];
+            zb[Pad8::at(n)] = c32{w * wa[n], hasb ? w * wa[n + kHopP] : 0.0f};
+          }
+        } else {
+          for (int n = env.lane; n < kNfftP; n += LANES) {
+            const float w = tb->win512[n];
+            zb[Pad8::at(n)] = c32{w * W(sa + n), hasb ? w * W(sb + n) : 0.0f};
+          }
         }
         env.wsync();
-        fft_stage<kNfftP, 8, 512, false, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 512, false, Pad8, LANES>(zb, tb->tw512_s1, env.lane);
         env.wsync();
-        fft_stage<kNfftP, 8, 64, false, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 64, false, Pad8, LANES>(zb, tb->tw512_s2, env.lane);
         env.wsync();
-        fft_stage<kNfftP, 8, 8, false, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 8, false, Pad8, LANES>(zb, nullptr, env.lane);
         env.wsync();
         // phase_vocoder(rate = 1.0) returns its input: the spectrum goes straight back
-        fft_stage<kNfftP, 8, 8, true, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 8, true, Pad8, LANES>(zb, nullptr, env.lane);
         env.wsync();
-        fft_stage<kNfftP, 8, 64, true, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 64, true, Pad8, LANES>(zb, tb->tw512_s2, env.lane);
         env.wsync();
-        fft_stage<kNfftP, 8, 512, true, Pad8>(zb, tb->tw512, env.lane, env.nlanes);
+        fft_stage<kNfftP, 8, 512, true, Pad8, LANES>(zb, tb->tw512_s1, env.lane);
       }
       env.sync();
       // overlap-add by gathering: every padded position sums the <= 4 frames of this batch that cover it
@@ -345,38 +368,44 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   {
     const float thr = gmax - 80.0f;
     const float* dct = P.tab->dct;
-    for (int fl = env.tid; fl < nfr; fl += env.nthreads) {
-      float acc[kMfcc];
-#pragma unroll
-      for (int k = 0; k < kMfcc; ++k) acc[k] = 0.0f;
+    // one thread per (frame, group of 4 coefficients): 13 = 4 + 4 + 4 + 1
+    for (int it = env.tid; it < nfr * 4; it += env.nthreads) {
+      const int fl = it >> 2, kg = it & 3;
       const float* row = dbs + fl * kDbStride;
+      const float* dk = dct + kg * 4;
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
       for (int m = 0; m < kMels; ++m) {
         const float v = fmaxf(row[m], thr);
-#pragma unroll
-        for (int k = 0; k < kMfcc; ++k) acc[k] = fmaf(v, dct[m * kDctStride + k], acc[k]);
+        const float* d = dk + m * kDctStride;
+        a0 = fmaf(v, d[0], a0);
+        a1 = fmaf(v, d[1], a1);                         // columns 13..15 of the padded table are zero
+        a2 = fmaf(v, d[2], a2);
+        a3 = fmaf(v, d[3], a3);
       }
-#pragma unroll
-      for (int k = 0; k < kMfcc; ++k) mfcc[fl * kMfcc + k] = acc[k];
-      if (P.dbg_mfcc) {
-        float* o = P.dbg_mfcc + ((size_t)seg * nFm + fm_begin + fl) * kMfcc;
-        for (int k = 0; k < kMfcc; ++k) o[k] = acc[k];
-      }
+      float* o = mfcc + fl * kMfcc + kg * 4;
+      o[0] = a0;
+      if (kg < 3) { o[1] = a1; o[2] = a2; o[3] = a3; }
     }
     env.sync();
-    double s = 0.0, ss = 0.0, alo = 0.0, ahi = 0.0;
+    if (P.dbg_mfcc) {
+      float* o = P.dbg_mfcc + ((size_t)seg * nFm + fm_begin) * kMfcc;
+      for (int i = env.tid; i < nfr * kMfcc; i += env.nthreads) o[i] = mfcc[i];
+    }
+    double ss = 0.0, alo = 0.0, ahi = 0.0;
     for (int i = env.tid; i < nfr * kMfcc; i += env.nthreads) {
       const double v = mfcc[i];
-      s += v; ss += v * v;
+      ss += v * v;
       if (i % kMfcc < 6) alo += fabs(v); else ahi += fabs(v);
     }
     ss = env.bsum(ss, red); alo = env.bsum(alo, red); ahi = env.bsum(ahi, red);
-    for (int k = env.tid; k < kMfcc; k += env.nthreads) {
+    // per-coefficient time sums: warp w reduces coefficient k = w, w + nwarps, ...
+    for (int k = env.warp; k < kMfcc; k += env.nwarps) {
       double sk = 0.0;
-      for (int fl = 0; fl < nfr; ++fl) sk += (double)mfcc[fl * kMfcc + k];
-      part->mf_sum[k] = sk;
+      for (int fl = env.lane; fl < nfr; fl += LANES) sk += (double)mfcc[fl * kMfcc + k];
+      sk = env.wsum(sk);
+      if (env.lane == 0) part->mf_sum[k] = sk;
     }
     if (env.tid == 0) { part->mf_sumsq = ss; part->mf_abs_lo = alo; part->mf_abs_hi = ahi; }
-    (void)s;
   }
   env.csync();                                            // #2: all partial moments and atoms are visible
 

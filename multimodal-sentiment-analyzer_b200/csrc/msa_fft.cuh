@@ -13,7 +13,7 @@
 
 namespace msa {
 
-struct c32 { float x, y; };
+struct alignas(8) c32 { float x, y; };   // 8-byte aligned: one LDS.64 / STS.64 per complex value
 MSA_FN c32 operator+(c32 a, c32 b) { return {a.x + b.x, a.y + b.y}; }
 MSA_FN c32 operator-(c32 a, c32 b) { return {a.x - b.x, a.y - b.y}; }
 MSA_FN c32 cmul(c32 a, c32 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
@@ -94,39 +94,43 @@ struct Pad8 { MSA_FN static int at(int i) { return i + (i >> 3); } };   // 512-p
 constexpr int kPad512 = 512 + 64;
 
 // One radix-R stage over an N-point transform whose current sub-transform size is NS.
-// tw = interleaved (cos, -sin) of 2*pi*k/N.  `lane`/`nlanes` distribute the N/R butterflies.
-template <int N, int R, int NS, bool INV, class P>
-MSA_FN void fft_stage(c32* zb, const float* tw, int lane, int nlanes) {
+// tw = per-stage twiddle table W_NS^(j*k) stored [k-1][j] as (cos, -sin); unused when m == 1.
+// LANES is the number of lanes sharing the N/R butterflies (32 on the GPU -> fully unrolled, 1 in the
+// CPU emulation); every lane's butterflies are independent, so the compiler can overlap their loads.
+template <int N, int R, int NS, bool INV, class P, int LANES>
+MSA_FN void fft_stage(c32* zb, const c32* tw, int lane) {
   constexpr int m = NS / R;
   constexpr int items = N / R;
-  constexpr int tstep = N / NS;
-  for (int it = lane; it < items; it += nlanes) {
-    const int b = it / m, j = it - b * m;
-    const int base = b * NS + j;
-    c32 v[R];
+  constexpr int per_lane = (items + LANES - 1) / LANES;
 #pragma unroll
-    for (int q = 0; q < R; ++q) v[q] = zb[P::at(base + q * m)];
-    if (INV) {
-      if (m > 1) {
+  for (int u = 0; u < per_lane; ++u) {
+    const int it = lane + u * LANES;
+    if (items % LANES == 0 || it < items) {
+      const int b = it / m, j = it - b * m;
+      const int base = b * NS + j;
+      c32 v[R];
 #pragma unroll
-        for (int k = 1; k < R; ++k) {
-          const int ti = j * k * tstep;
-          v[k] = cmulc(v[k], c32{tw[2 * ti], tw[2 * ti + 1]});
+      for (int q = 0; q < R; ++q) v[q] = zb[P::at(base + q * m)];
+      if (INV) {
+        if (m > 1) {
+#pragma unroll
+          for (int k = 1; k < R; ++k) {
+            v[k] = cmulc(v[k], tw[(k - 1) * m + j]);
+          }
+        }
+        dftR<R, true>(v);
+      } else {
+        dftR<R, false>(v);
+        if (m > 1) {
+#pragma unroll
+          for (int k = 1; k < R; ++k) {
+            v[k] = cmul(v[k], tw[(k - 1) * m + j]);
+          }
         }
       }
-      dftR<R, true>(v);
-    } else {
-      dftR<R, false>(v);
-      if (m > 1) {
 #pragma unroll
-        for (int k = 1; k < R; ++k) {
-          const int ti = j * k * tstep;
-          v[k] = cmul(v[k], c32{tw[2 * ti], tw[2 * ti + 1]});
-        }
-      }
+      for (int q = 0; q < R; ++q) zb[P::at(base + q * m)] = v[q];
     }
-#pragma unroll
-    for (int q = 0; q < R; ++q) zb[P::at(base + q * m)] = v[q];
   }
 }
 

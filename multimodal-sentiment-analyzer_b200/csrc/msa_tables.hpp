@@ -29,11 +29,15 @@ constexpr int kDctStride = 16;                           // 13 coefficients padd
 struct FeatureTables {
   float win400[kNfftM];
   float win512[kNfftP];
-  float tw400[2 * kNfftM];        // (cos, -sin) of 2*pi*k/400, interleaved
-  float tw512[2 * kNfftP];
+  // per-stage twiddles W_NS^(j*k) stored [k-1][j] (consecutive lanes -> consecutive words), (cos, -sin)
+  float tw512_s1[2 * 7 * 64];     // NS = 512, radix 8, m = 64
+  float tw512_s2[2 * 7 * 8];      // NS = 64,  radix 8, m = 8
+  float tw400_s1[2 * 15 * 25];    // NS = 400, radix 16, m = 25
+  float tw400_s2[2 * 4 * 5];      // NS = 25,  radix 5, m = 5
   uint16_t perm400[kNfftM];       // position in the DIF output that holds bin k (radices 16,5,5)
   uint16_t mel_ptr[kMels + 1];    // CSR row pointers per mel filter
   uint16_t mel_bin[kMelNnzMax];
+  uint16_t mel_pos[2 * kMelNnzMax];   // (position of bin k, position of bin N-k) in the DIF output, per non-zero
   float mel_w[kMelNnzMax];
   float dct[kMels * kDctStride];  // dct[m*16 + k], k < 13
 };
@@ -43,14 +47,19 @@ inline void build_feature_tables(FeatureTables& t) {
   const double PI = 3.14159265358979323846;
   for (int n = 0; n < kNfftM; ++n) t.win400[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftM));
   for (int n = 0; n < kNfftP; ++n) t.win512[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP));
-  for (int k = 0; k < kNfftM; ++k) {
-    t.tw400[2 * k] = (float)std::cos(2.0 * PI * k / kNfftM);
-    t.tw400[2 * k + 1] = (float)(-std::sin(2.0 * PI * k / kNfftM));
-  }
-  for (int k = 0; k < kNfftP; ++k) {
-    t.tw512[2 * k] = (float)std::cos(2.0 * PI * k / kNfftP);
-    t.tw512[2 * k + 1] = (float)(-std::sin(2.0 * PI * k / kNfftP));
-  }
+  auto fill = [&](float* dst, int NS, int R) {
+    const int m = NS / R;
+    for (int k = 1; k < R; ++k)
+      for (int j = 0; j < m; ++j) {
+        const double a = 2.0 * PI * (double)(j * k) / NS;
+        dst[2 * ((k - 1) * m + j)] = (float)std::cos(a);
+        dst[2 * ((k - 1) * m + j) + 1] = (float)(-std::sin(a));
+      }
+  };
+  fill(t.tw512_s1, 512, 8);
+  fill(t.tw512_s2, 64, 8);
+  fill(t.tw400_s1, 400, 16);
+  fill(t.tw400_s2, 25, 5);
   // digit reversal of the in-place DIF with radices (16, 5, 5): position p = d1*25 + d2*5 + d3
   // holds bin k = d1 + 16*d2 + 80*d3.
   for (int p = 0; p < kNfftM; ++p) {
@@ -84,6 +93,11 @@ inline void build_feature_tables(FeatureTables& t) {
       }
     }
     t.mel_ptr[kMels] = (uint16_t)nnz;
+    for (int p = 0; p < nnz; ++p) {
+      const int k = t.mel_bin[p];
+      t.mel_pos[2 * p] = t.perm400[k];
+      t.mel_pos[2 * p + 1] = t.perm400[(kNfftM - k) % kNfftM];
+    }
   }
   // DCT-II ortho (torchaudio.functional.create_dct(13, 128, "ortho")), stored [mel][16]
   for (int m = 0; m < kMels; ++m)

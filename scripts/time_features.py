@@ -1,0 +1,28 @@
+"""Time the feature kernel alone (CUDA events) for the current MSA_FEAT_* environment."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import msa_b200
+from msa_b200 import _lib
+from oracle import synth
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+dtype = sys.argv[2] if len(sys.argv) > 2 else "f32"
+dev = torch.device("cuda:0")
+ana = msa_b200.AudioAnalyzer(device="cuda:0")
+pcm = torch.from_numpy(synth.fast_segments_pcm(3, B)).to(dev)
+wav = pcm if dtype == "s16" else (pcm.float() / 32768.0).contiguous()
+feat = torch.empty(B, 31, device=dev)
+lib = _lib.lib()
+fn = lib.msa_features_s16 if dtype == "s16" else lib.msa_features_f32
+def run():
+    rc = fn(_lib.ptr(wav), B, 80000, None, _lib.ptr(feat), None, None, ana._flags(), 7, 0, None)
+    assert rc == 0, rc
+for _ in range(3): run()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): run()
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print(f"threads={os.environ.get('MSA_FEAT_THREADS','dflt')} slice={os.environ.get('MSA_FEAT_SLICE','dflt')} cluster={lib.msa_features_cluster_size(80000)} "
+      f"B={B} {dtype}: {ms:.3f} ms  -> {B*5/ms*1e3/1e6:.2f} M audio-s/s, {320124*B/ms/1e6:.1f} GB/s algorithmic")

@@ -26,6 +26,7 @@ struct CpuCluster {
 };
 
 struct CpuEnv {
+  static constexpr int kLanes = 1;
   int tid, nthreads, lane, nlanes, warp, nwarps, rank, nranks, cluster_id;
   std::barrier<>* block;
   CpuCluster* cl;
