@@ -152,6 +152,29 @@ def test_pipeline_and_aggregation():
         assert got == starts
 
 
+def test_host_buffer_pipeline_equals_resident():
+    """SegmentPipeline.run_host (chunked upload overlapped with compute) == run on resident tensors,
+    with a ragged last chunk and with/without text."""
+    dev = need_gpu()
+    import msa_b200
+    from msa_b200.pipeline import ROW_WORDS
+    ana = msa_b200.AudioAnalyzer(device="cuda:0")
+    m, _ = _model(True, 0)
+    n = 21
+    pcm = torch.from_numpy(synth.fast_segments_pcm(5, n)).pin_memory()
+    face = torch.from_numpy(synth.face_rows(6, n)).pin_memory()
+    text = torch.from_numpy(synth.text_rows(7, n)).pin_memory()
+    pipe = msa_b200.SegmentPipeline(ana, m)
+    for tx in (text, None):
+        out = torch.zeros(n, ROW_WORDS).pin_memory()
+        for _ in range(2):                                   # second pass re-uses the double buffer
+            pipe.run_host(pcm, face, tx, out, first_id=7, chunk=8)
+        torch.cuda.synchronize()
+        ref = pipe.run(pcm.to(dev), face.to(dev), None if tx is None else tx.to(dev), first_id=7)
+        torch.cuda.synchronize()
+        assert torch.equal(out.view(torch.int32), ref.cpu().view(torch.int32))
+
+
 def test_streaming_window_equals_offline():
     dev = need_gpu()
     import msa_b200
