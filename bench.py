@@ -173,7 +173,7 @@ def run_native(args):
     import msa_b200
     from msa_b200 import _lib
     from msa_b200.pipeline import ROW_WORDS, gather_rows, pack_rows
-    from oracle import synth
+    from msa_b200 import synth
 
     S = args.segments
     ana = msa_b200.AudioAnalyzer(device=str(dev))

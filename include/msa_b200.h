@@ -33,7 +33,7 @@ extern "C" {
 
 /* flags of msa_features_* */
 #define MSA_FEAT_STRICT_NAN 1 /* mono intensity = NaN exactly like audio_analyzer.py:194-196 (default) */
-#define MSA_FEAT_BULK_COPY 2  /* stage fp32 slices with TMA bulk copies (cp.async.bulk) */
+#define MSA_FEAT_BULK_COPY 2  /* reserved (accepted and ignored): the waveform is no longer staged in shared memory */
 /* parts mask: which feature groups to compute (the rest take the reference's exception defaults) */
 #define MSA_PART_WAVE 1  /* rhythm, speech_rate, snr, consistency */
 #define MSA_PART_MFCC 2  /* timbre, clarity */
@@ -45,8 +45,9 @@ extern "C" {
 int msa_version(void);
 const char* msa_strerror(int code);
 
-/* Number of CTAs per cluster msa_features_* will use for segments of T samples (0 if T is
- * unsupported), and the dynamic shared memory per CTA.  For capacity planning / tests. */
+/* Smallest number of CTAs per cluster that can hold a segment of T samples (0 if T is unsupported;
+ * a 5 s segment needs 1), and the dynamic shared memory per CTA.  With cluster_size = 0 the launch
+ * uses this value for large batches and up to 8 CTAs per segment when B is small (streaming). */
 int msa_features_cluster_size(int T);
 int msa_features_smem_bytes(int T, int cluster_size);
 
@@ -64,9 +65,9 @@ int msa_features_smem_bytes(int T, int cluster_size);
  *   detail  [B, 96] out or NULL: [0:27] raw features before LayerNorm in analyze()'s concat order
  *           (emotion8, pitch, intensity, timbre13, speech_rate, rhythm3), [27:31] the four quality
  *           floats, [32:63] the full LayerNorm(31) row (NaN where the reference is NaN),
- *           [64:75] diagnostics (top_db max, residual mean/std/max, energies, counts)
+ *           [64:77] diagnostics (top_db max, residual mean/std/max, energies, counts, clamped-pass flag, min dB)
  *   dbg_mfcc [B, T/200+1, 13] out or NULL: the MFCC matrix (frames x coefficients)
- *   cluster_size 0 = auto (msa_features_cluster_size), else 1/2/4/8/16
+ *   cluster_size 0 = auto, else 1/2/4/8
  */
 int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
                      float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream);

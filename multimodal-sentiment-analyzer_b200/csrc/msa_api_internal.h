@@ -3,8 +3,8 @@
 #include "../../include/msa_b200.h"
 
 namespace msa {
-constexpr int kFeatThreads = 256;      // default threads per feature CTA (8 warps; fastest in profiles/tune_r1)
-constexpr int kFeatSlicePref = 20000;  // default preferred samples per CTA (5 s segment -> cluster of 4)
+constexpr int kFeatThreads = 512;      // default threads per feature CTA (16 warps x <= 128 registers)
+constexpr int kNumSms = 148;
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in shared memory per CTA on sm_100
 void reset_launches();
 void note_launches(int n);

@@ -1,6 +1,6 @@
-// Device execution environment for msa_features_body.cuh: 32-lane warps, block barriers,
-// thread-block cluster barriers and distributed shared memory (DSMEM), and the slice loader
-// (TMA bulk copy global -> shared when the fp32 source is 16-byte aligned).
+// Device execution environment for msa_features_body.cuh: 32-lane warps (per-lane state lives in
+// registers, so there is ONE state copy and lanes() runs its body once), block barriers,
+// thread-block cluster barriers and distributed shared memory (DSMEM), read-only global loads.
 #pragma once
 #include <cooperative_groups.h>
 #include <cstdint>
@@ -9,116 +9,60 @@
 namespace msa {
 namespace cg = cooperative_groups;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 struct GpuEnv {
-  static constexpr int kLanes = 32;
-  int tid, nthreads, lane, nlanes, warp, nwarps, rank, nranks, cluster_id;
+  static constexpr int kStates = 1;
+  int tid, nthreads, lane, warp, nwarps, rank, nranks, cluster_id;
 
+  template <class F> __device__ __forceinline__ void lanes(F&& f) { f(lane, 0); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
   __device__ __forceinline__ void wsync() { __syncwarp(); }
   __device__ __forceinline__ void csync() { cg::this_cluster().sync(); }
   template <class T> __device__ __forceinline__ T* remote(T* p, int r) {
     return cg::this_cluster().map_shared_rank(p, r);
   }
-  __device__ __forceinline__ double wsum(double v) {
+  __device__ __forceinline__ float log2(float v) { return __log2f(v); }
+
+  // one sample as fp32 (int16 PCM is scaled by 1/32768 like torchaudio.load)
+  __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  __device__ __forceinline__ float ld(const int16_t* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
+
+  // samples idx .. idx+3 of a segment of T samples (0 beyond the end), one vector load when aligned
+  __device__ __forceinline__ void ld4(const float* x, int idx, int T, float* v) {
+    const float* p = x + idx;
+    if (idx + 3 < T && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-  }
-  __device__ __forceinline__ float wmax(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  }
-  __device__ __forceinline__ double bsum(double v, double* red) {
-    v = wsum(v);
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += red[w];
-    __syncthreads();
-    return s;
-  }
-  __device__ __forceinline__ float bmax(float v, double* red) {
-    float* r = reinterpret_cast<float*>(red);
-    v = wmax(v);
-    if (lane == 0) r[warp] = v;
-    __syncthreads();
-    float s = r[0];
-    for (int w = 1; w < nwarps; ++w) s = fmaxf(s, r[w]);
-    __syncthreads();
-    return s;
-  }
-
-  // Stage n samples of the segment slice into shared memory as fp32.
-  template <class InT>
-  __device__ __forceinline__ void load_slice(float* dst, const InT* src, int n, void* bar_mem, bool bulk);
-};
-
-template <>
-__device__ __forceinline__ void GpuEnv::load_slice<float>(float* dst, const float* src, int n, void* bar_mem, bool bulk) {
-  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  int done = 0;
-  if (bulk && aligned && n >= 4) {
-    // TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP), completion counted in bytes on an mbarrier
-    const uint32_t bar = smem_u32(bar_mem);
-    const int nb = (n & ~3) * 4;
-    if (tid == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? __ldg(p + i) : 0.0f;
     }
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
-      const int chunk = 16384;
-      for (int off = 0; off < nb; off += chunk) {
-        const int sz = (nb - off < chunk) ? nb - off : chunk;
-        asm volatile(
-            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                smem_u32(reinterpret_cast<unsigned char*>(dst) + off)),
-            "l"(reinterpret_cast<const unsigned char*>(src) + off), "r"(sz), "r"(bar)
-            : "memory");
-      }
-    }
-    uint32_t ok = 0;
-    while (!ok) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-          : "=r"(ok)
-          : "r"(bar), "r"(0)
-          : "memory");
-    }
-    done = n & ~3;
-  } else if (aligned) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    for (int i = tid; i < n / 4; i += nthreads) d4[i] = __ldg(s4 + i);
-    done = n & ~3;
   }
-  for (int i = done + tid; i < n; i += nthreads) dst[i] = __ldg(src + i);
-}
-
-template <>
-__device__ __forceinline__ void GpuEnv::load_slice<int16_t>(float* dst, const int16_t* src, int n, void*, bool) {
-  const bool aligned = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-  int done = 0;
-  if (aligned) {
-    const int4* s8 = reinterpret_cast<const int4*>(src);
+  __device__ __forceinline__ void ld4(const int16_t* x, int idx, int T, float* v) {
+    const int16_t* p = x + idx;
     const float k = 1.0f / 32768.0f;
-    for (int i = tid; i < n / 8; i += nthreads) {
-      const int4 v = __ldg(s8 + i);
-      float4 a, b;
-      a.x = (float)(short)(v.x & 0xffff) * k; a.y = (float)(short)(v.x >> 16) * k;
-      a.z = (float)(short)(v.y & 0xffff) * k; a.w = (float)(short)(v.y >> 16) * k;
-      b.x = (float)(short)(v.z & 0xffff) * k; b.y = (float)(short)(v.z >> 16) * k;
-      b.z = (float)(short)(v.w & 0xffff) * k; b.w = (float)(short)(v.w >> 16) * k;
-      reinterpret_cast<float4*>(dst)[2 * i] = a;
-      reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+    if (idx + 3 < T && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+      const int2 q = __ldg(reinterpret_cast<const int2*>(p));
+      v[0] = (float)(short)(q.x & 0xffff) * k; v[1] = (float)(short)(q.x >> 16) * k;
+      v[2] = (float)(short)(q.y & 0xffff) * k; v[3] = (float)(short)(q.y >> 16) * k;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? (float)__ldg(p + i) * k : 0.0f;
     }
-    done = n & ~7;
   }
-  for (int i = done + tid; i < n; i += nthreads) dst[i] = (float)__ldg(src + i) * (1.0f / 32768.0f);
-}
+
+  // block-wide copy of a 16-byte aligned table into shared memory
+  __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes) {
+    const int4* s = reinterpret_cast<const int4*>(src);
+    int4* d = reinterpret_cast<int4*>(dst);
+    for (int i = tid; i < bytes / 16; i += nthreads) d[i] = __ldg(s + i);
+  }
+
+  // dynamic work distribution: one shared-memory counter per CTA, one atomic per warp and task
+  __device__ __forceinline__ int next_task(int* ctr) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(ctr, 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+  }
+};
 
 }  // namespace msa

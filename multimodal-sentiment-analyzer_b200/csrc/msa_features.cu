@@ -17,7 +17,6 @@ __global__ void __launch_bounds__(THREADS, 1) features_kernel(const FeatParams P
   env.tid = threadIdx.x;
   env.nthreads = blockDim.x;
   env.lane = threadIdx.x & 31;
-  env.nlanes = 32;
   env.warp = threadIdx.x >> 5;
   env.nwarps = blockDim.x >> 5;
   env.rank = (int)cluster.block_rank();
@@ -49,13 +48,7 @@ static int get_tables(const FeatureTables** out) {
   return MSA_OK;
 }
 
-static int slice_len_for(int T, int c) {
-  int L = (T + c - 1) / c;
-  return ((L + kAtom - 1) / kAtom) * kAtom;
-}
-
-// Tuning knobs (read once): MSA_FEAT_THREADS = 256 | 512 threads per CTA, MSA_FEAT_SLICE = preferred
-// samples per CTA (the cluster grows until a slice is at most this long and fits shared memory).
+// Tuning knob (read once): MSA_FEAT_THREADS = 256 | 512 threads per CTA.
 static int env_int(const char* name, int dflt) {
   const char* e = std::getenv(name);
   return (e && *e) ? std::atoi(e) : dflt;
@@ -64,26 +57,29 @@ int feat_threads() {
   static const int t = (env_int("MSA_FEAT_THREADS", kFeatThreads) == 256) ? 256 : 512;
   return t;
 }
-static int feat_slice_pref() {
-  static const int s = env_int("MSA_FEAT_SLICE", kFeatSlicePref);
-  return s;
-}
 
+// Smallest cluster whose per-CTA shared-memory layout fits (the per-segment MFCC tile and the energy
+// atoms are split over the ranks; everything else is per warp).
 int features_cluster_size(int T) {
   if (T < 1) return 0;
   const int nwarps = feat_threads() / 32;
-  for (int c = 1; c <= 16; c *= 2) {
-    const int L = slice_len_for(T, c);
-    if (L <= feat_slice_pref() && feat_layout(L, nwarps).total <= kMaxSmem) return c;
-  }
-  for (int c = 1; c <= 16; c *= 2)
-    if (feat_layout(slice_len_for(T, c), nwarps).total <= kMaxSmem) return c;
+  for (int c = 1; c <= 8; c *= 2)
+    if (feat_layout(T, c, nwarps).total <= kMaxSmem) return c;
   return 0;
+}
+
+// Few segments (streaming: B = 1) spread over more CTAs to cut latency; large batches use the smallest
+// cluster so that the quad lists per CTA stay long.
+static int auto_cluster_size(int B, int T) {
+  int c = features_cluster_size(T);
+  if (c == 0) return 0;
+  while (c < 8 && (long long)B * c * 2 <= kNumSms) c *= 2;
+  return c;
 }
 
 int features_smem_bytes(int T, int c) {
   if (T < 1 || c < 1) return 0;
-  return feat_layout(slice_len_for(T, c), feat_threads() / 32).total;
+  return feat_layout(T, c, feat_threads() / 32).total;
 }
 
 template <class InT>
@@ -91,8 +87,8 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
                            float* dbg_mfcc, int flags, int parts, int cluster_size, cudaStream_t stream) {
   if (!wav || !feat31 || B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
   if (B == 0) return MSA_OK;
-  int c = cluster_size ? cluster_size : features_cluster_size(T);
-  if (c != 1 && c != 2 && c != 4 && c != 8 && c != 16) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
+  int c = cluster_size ? cluster_size : auto_cluster_size(B, T);
+  if (c != 1 && c != 2 && c != 4 && c != 8) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
   // torch.stft's reflect padding needs T > n_fft/2: below that the reference's method raises and
   // returns its default, which is what a cleared part bit produces.
   if (T <= kNfftP / 2) parts &= ~kPartPitch;
@@ -106,7 +102,6 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.is_s16 = sizeof(InT) == 2;
   P.B = B;
   P.T = T;
-  P.slice_len = slice_len_for(T, c);
   P.noise_n = (int)(0.05 * (double)T);   // int(0.05 * waveform.shape[1]), audio_analyzer.py:282
   P.emo8 = emo8;
   P.feat31 = feat31;
@@ -116,16 +111,12 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.flags = flags;
   P.parts = parts;
   const int threads = feat_threads();
-  const FeatLayout lay = feat_layout(P.slice_len, threads / 32);
+  const FeatLayout lay = feat_layout(T, c, threads / 32);
   if (lay.total > kMaxSmem) return MSA_ERR_UNSUPPORTED_LENGTH;
 
   auto kern = (threads == 256) ? features_kernel<InT, 256> : features_kernel<InT, 512>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
   if (e != cudaSuccess) return (int)e;
-  if (c > 8) {
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return (int)e;
-  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)B * c, 1, 1);
   cfg.blockDim = dim3(threads, 1, 1);

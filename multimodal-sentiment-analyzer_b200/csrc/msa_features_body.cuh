@@ -1,4 +1,4 @@
-// Fused audio-feature kernel body: one thread-block CLUSTER per 5 s segment.
+// Fused audio-feature kernel body: one thread-block CLUSTER (1, 2, 4 or 8 CTAs) per 5 s segment.
 //
 // Restates, for one mono segment [T], what AudioAnalyzer computes per call
 // (/root/reference/src/analyzers/audio_analyzer.py):
@@ -12,19 +12,32 @@
 //   AudioFeatureNormalizer.normalize (src/utils/normalization.py:26-44) -> LayerNorm(31)
 //   audio row for fusion (src/processors/streaming_processor.py:250-268, 295-298)
 //
-// Work split: the segment's samples [0,T) are cut into `nranks` contiguous slices; CTA `rank`
-// stages its slice (+512-sample halos) in shared memory ONCE (the only HBM read of the
-// waveform) and computes, from shared memory, every MFCC frame whose centre, every output
-// sample of the STFT->ISTFT round trip and every 80-sample energy atom that falls in its slice.
-// The whole-segment dependencies (top_db max, z-score moments, frame-energy statistics) are
+// Work unit = one WARP x one QUAD of four consecutive STFT frames, i.e. two complex FFTs with
+// two real frames packed in each (re, im).  Every FFT pass runs in registers (msa_fft.cuh):
+//   pass A   lane n2 : 16 strided samples x window -> radix-16 -> inter-pass twiddle -> smem [k1][n2]
+//   pass B   lane k1 : one row -> radix-32 (radix-25 for n_fft 400); lanes 0-15 serve the first
+//            FFT of the quad, lanes 16-31 the second, so every lane is busy
+// so a transform crosses shared memory once per direction.  The waveform is read straight from
+// global memory (each 128-byte line reaches the SM from HBM once and is re-read from L1 by the
+// overlapping frames); nothing but constant tables and small per-warp tiles lives in shared memory.
+//
+//   "pitch"  B is followed at once, in the same registers, by the inverse radix-32 (the vocoder at
+//            rate 1.0 returns its input), then the inverse pass A, the synthesis window and the
+//            overlap-add of the quad's 4 frames in registers.  The 3 hop-blocks that overlap the
+//            next quad travel through a 1.5 KB shared-memory tile per warp.
+//   MFCC     power of both packed frames from Z_k and Z_(N-k), sparse mel (each lane owns 4 filters),
+//            dB, and the lane's share of the DCT; a 52 x 32 shared-memory transpose sums the shares.
+//            top_db needs the segment maximum, which is only known after the last frame: the DCT is
+//            linear, the four EMPTY mel filters sit at max(-100, max-80) dB for every frame and enter
+//            as one constant vector afterwards, and a live filter below max-80 dB (digital silence
+//            inside a loud segment) triggers a second, clamped MFCC pass.
+//
+// Whole-segment dependencies (top_db maximum, z-score moments, frame-energy statistics) are
 // exchanged through distributed shared memory; rank 0 assembles the 31-float row.
 //
-// FFTs: one warp per transform, in place in shared memory, two real frames packed into one
-// complex transform (msa_fft.cuh).  Warps run independently; only the overlap-add of the ISTFT
-// needs block barriers (once per batch of 2*nwarps frames).
-//
-// This file is compiled by nvcc (GpuEnv, msa_features.cu) and by g++ (CpuEnv, tests/emu)
-// so the index logic can be exercised without a GPU.  It must only use the Env primitives.
+// This file is compiled by nvcc (GpuEnv, msa_features.cu) and by g++ (CpuEnv, tests/emu: the 32
+// lanes of a warp run sequentially between warp barriers, one OS thread per warp) so the index
+// logic can be exercised without a GPU.  It must only use the Env primitives.
 #pragma once
 #include <cstdint>
 #include "msa_fft.cuh"
@@ -33,18 +46,21 @@
 
 namespace msa {
 
-constexpr int kHalo = 512;
-constexpr int kDbStride = kMels + 1;       // 129: conflict-free row-per-thread reads in the DCT step
 constexpr int kDetailStride = 96;
+constexpr int kRow512 = 33, kRow400 = 25;        // row strides (complex words) of the pass-A -> pass-B tiles
+constexpr int kFftHalf = 16 * kRow512;           // one FFT tile: 528 complex = 4224 bytes
+constexpr int kWarpBufBytes = 2 * kFftHalf * 8;  // two tiles per warp
+constexpr int kTailFloats = 3 * kHopP;           // the 3 hop-blocks a quad leaves to its successor
+constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
+constexpr int kRedSlots = 16;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
-enum : int { kFlagStrictNan = 1, kFlagBulkCopy = 2 };
+enum : int { kFlagStrictNan = 1 };
 
 struct FeatParams {
   const void* wav;       // [B, T] fp32 or int16
   int is_s16;
   int B, T;
-  int slice_len;         // samples per cluster rank, multiple of 80
   int noise_n;           // int(0.05 * T) computed by the host exactly like the reference
   const float* emo8;     // [B, 8] or null -> 1/8
   float* feat31;         // [B, 31]  LN31[:27] ++ quality4, nan_to_num'd (fusion input row)
@@ -55,31 +71,18 @@ struct FeatParams {
   int parts;
 };
 
-// tables staged in shared memory (the DCT matrix stays in global: warp-uniform reads through L1)
-struct SmemTables {
-  c32 tw512_s1[7 * 64];
-  c32 tw512_s2[7 * 8];
-  c32 tw400_s1[15 * 25];
-  c32 tw400_s2[4 * 5];
-  float win400[kNfftM];
-  float win512[kNfftP];
-  float mel_w[kMelNnzMax];
-  uint16_t mel_pos[2 * kMelNnzMax];
-  uint16_t mel_ptr[kMels + 2];
-};
-
 struct Partials {
   double mf_sum[kMfcc];
   double mf_sumsq, mf_abs_lo, mf_abs_hi;
   double p_n, p_sum, p_sumsq;
   double e_total, e_noise;
-  float db_max, p_max;
-  int mf_frames, n_atoms;
+  float db_max, db_min, p_max;
+  int mf_frames, n_atoms, slow_pass;
 };
 
 struct FeatLayout {
-  int wave_off, zb_off, dbs_off, mfcc_off, carry_off, atoms_off, tab_off, red_off, part_off, bar_off;
-  int wave_cap, dbs_rows, total;
+  int buf_off, tail_off, mfl_off, atoms_off, tab_off, out_off, part_off, ctr_off;
+  int mfl_frames, atoms_cap, total;
 };
 
 MSA_FN int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -89,29 +92,29 @@ inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-FeatLayout feat_layout(int slice_len, int nwarps) {
+FeatLayout feat_layout(int T, int nranks, int nwarps) {
   FeatLayout l;
   int off = 0;
   auto take = [&](int bytes) { int o = off; off += (bytes + 15) & ~15; return o; };
-  l.wave_cap = slice_len + 2 * kHalo;
-  l.dbs_rows = slice_len / kHopM + 2;
-  l.wave_off = take(l.wave_cap * 4);
-  l.zb_off = take(nwarps * kPad512 * 8);
-  l.dbs_off = take(l.dbs_rows * kDbStride * 4);
-  l.mfcc_off = take(l.dbs_rows * kMfcc * 4);
-  l.carry_off = take(2 * 3 * kHopP * 4);
-  l.atoms_off = take((slice_len / kAtom + 1) * 4);
+  const int nFm = T / kHopM + 1;
+  l.mfl_frames = 4 * ((((nFm + 3) / 4) + nranks - 1) / nranks);
+  l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
+  int buf = nwarps * kWarpBufBytes;
+  const int red = (kRedSlots * (nwarps * 32 + 32)) * 8;        // block-reduction scratch aliases the FFT tiles
+  const int gather = (T / kAtom + 8) * 4;                      // rank 0 gathers all energy atoms there at the end
+  if (buf < red) buf = red;
+  if (buf < gather) buf = gather;
+  l.buf_off = take(buf);
+  l.tail_off = take((nwarps + 1) * kTailFloats * 4);
+  l.mfl_off = take(l.mfl_frames * kMfcc * 4);
+  l.atoms_off = take(l.atoms_cap * 4);
   l.tab_off = take((int)sizeof(SmemTables));
-  l.red_off = take(64 * 8);
+  l.out_off = take(kRedSlots * 8);
   l.part_off = take((int)sizeof(Partials));
-  l.bar_off = take(16);
+  l.ctr_off = take(16);
   l.total = off;
   return l;
 }
-
-template <class InT> MSA_FN float to_f32(InT v);
-template <> MSA_FN float to_f32<float>(float v) { return v; }
-template <> MSA_FN float to_f32<int16_t>(int16_t v) { return (float)v * (1.0f / 32768.0f); }
 
 // python semantics of min(max(v, 0), 1): max(v,0) returns v unless 0 > v; min(w,1) returns w unless 1 < w
 MSA_FN double py_clip01(double v) {
@@ -119,349 +122,589 @@ MSA_FN double py_clip01(double v) {
   return (1.0 < w) ? 1.0 : w;
 }
 
+// ---- FFT passes (see msa_fft.cuh) ------------------------------------------------------------
+// pass A forward: 16 packed samples -> radix-16 -> twiddle W_N^(n2 k1) -> tile[k1][n2]
+template <int ROW> MSA_FN void pass_a_fwd(c32* z, const c32* tw, int n2, c32* tile) {
+  dft16<false>(z);
+  tile[n2] = z[0];
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) tile[k1 * ROW + n2] = cmul(z[k1], tw[(k1 - 1) * 32 + n2]);
+}
+// pass A inverse: tile[k1][n2] x conj twiddle -> inverse radix-16 -> 16 samples (unnormalised)
+template <int ROW> MSA_FN void pass_a_inv(c32* z, const c32* tw, int n2, const c32* tile) {
+  z[0] = tile[n2];
+#pragma unroll
+  for (int k1 = 1; k1 < 16; ++k1) z[k1] = cmulc(tile[k1 * ROW + n2], tw[(k1 - 1) * 32 + n2]);
+  dft16<true>(z);
+}
+
+enum : int { kOpSum = 0, kOpMax = 1, kOpMin = 2 };
+MSA_FN double red_comb(int op, double a, double b) {
+  return op == kOpSum ? a + b : (op == kOpMax ? (a > b ? a : b) : (a < b ? a : b));
+}
+
+// Deterministic block reduction of K per-lane doubles: out[k] (shared memory) = op_k over all threads.
+template <int K, class Env, class Get>
+MSA_KFN void block_reduce(Env& env, double* red, double* out, const int* ops, Get get) {
+  static_assert(K <= kRedSlots, "reduction scratch");
+  const int NT = env.nthreads;
+  env.lanes([&](int lane, int li) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) red[k * NT + env.warp * 32 + lane] = get(li, k);
+  });
+  env.sync();
+  if (env.warp == 0) {
+    env.lanes([&](int lane, int li) {
+      (void)li;
+      for (int k = 0; k < K; ++k) {
+        double a = red[k * NT + lane];
+        for (int w = 1; w < env.nwarps; ++w) a = red_comb(ops[k], a, red[k * NT + w * 32 + lane]);
+        red[K * NT + k * 32 + lane] = a;
+      }
+    });
+    env.wsync();
+    env.lanes([&](int lane, int li) {
+      (void)li;
+      if (lane < K) {
+        double a = red[K * NT + lane * 32];
+        for (int j = 1; j < 32; ++j) a = red_comb(ops[lane], a, red[K * NT + lane * 32 + j]);
+        out[lane] = a;
+      }
+    });
+  }
+  env.sync();
+}
+
 template <class Env, class InT>
 MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
-  constexpr int LANES = Env::kLanes;
-  const int T = P.T, L = P.slice_len;
-  const int seg = env.cluster_id, r = env.rank;
-  const int t0 = (r * L < T) ? r * L : T;
-  const int t1 = (t0 + L < T) ? t0 + L : T;
-  const bool has = t1 > t0;
-  const int lo = (t0 - kHalo > 0) ? t0 - kHalo : 0;
-  const int hi = (t1 + kHalo < T) ? t1 + kHalo : T;
-  const FeatLayout lay = feat_layout(L, env.nwarps);
+  constexpr int S = Env::kStates;           // per-lane state copies: 1 on the GPU (registers), 32 in the CPU emulation
+  const int T = P.T;
+  const int seg = env.cluster_id, r = env.rank, NR = env.nranks, NW = env.nwarps;
+  const FeatLayout lay = feat_layout(T, NR, NW);
+  const InT* x = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T;
 
-  float* wave = reinterpret_cast<float*>(smem + lay.wave_off);
-  c32* zb_all = reinterpret_cast<c32*>(smem + lay.zb_off);
-  float* dbs = reinterpret_cast<float*>(smem + lay.dbs_off);
-  float* mfcc = reinterpret_cast<float*>(smem + lay.mfcc_off);
-  float* carry = reinterpret_cast<float*>(smem + lay.carry_off);
+  c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
+  double* red = reinterpret_cast<double*>(smem + lay.buf_off);
+  float* tails = reinterpret_cast<float*>(smem + lay.tail_off);
+  float* mfl = reinterpret_cast<float*>(smem + lay.mfl_off);
   float* atoms = reinterpret_cast<float*>(smem + lay.atoms_off);
-  SmemTables* tb = reinterpret_cast<SmemTables*>(smem + lay.tab_off);
-  double* red = reinterpret_cast<double*>(smem + lay.red_off);
+  const SmemTables* tb = reinterpret_cast<const SmemTables*>(smem + lay.tab_off);
+  double* rout = reinterpret_cast<double*>(smem + lay.out_off);
   Partials* part = reinterpret_cast<Partials*>(smem + lay.part_off);
+  int* ctr = reinterpret_cast<int*>(smem + lay.ctr_off);
+  const c32* tw512 = reinterpret_cast<const c32*>(tb->tw512);
+  const c32* tw400 = reinterpret_cast<const c32*>(tb->tw400);
 
-  // reflect-101 indexing of torch.stft(center=True, pad_mode="reflect") into the staged slice
-  auto W = [&](int t) -> float {
+  // reflect-101 padded signal of torch.stft(center=True, pad_mode="reflect"); 0 outside the padding
+  auto xr = [&](int t) -> float {
     if (t < 0) t = -t;
     else if (t >= T) t = 2 * (T - 1) - t;
-    return wave[t - lo];
+    return (t >= 0 && t < T) ? env.ld(x + t) : 0.0f;
   };
 
-  // ---------------------------------------------------------------- stage tables + slice
-  {
-    const FeatureTables* g = P.tab;
-    const c32* s1 = reinterpret_cast<const c32*>(g->tw512_s1);
-    const c32* s2 = reinterpret_cast<const c32*>(g->tw512_s2);
-    const c32* m1 = reinterpret_cast<const c32*>(g->tw400_s1);
-    const c32* m2 = reinterpret_cast<const c32*>(g->tw400_s2);
-    for (int i = env.tid; i < 7 * 64; i += env.nthreads) tb->tw512_s1[i] = s1[i];
-    for (int i = env.tid; i < 7 * 8; i += env.nthreads) tb->tw512_s2[i] = s2[i];
-    for (int i = env.tid; i < 15 * 25; i += env.nthreads) tb->tw400_s1[i] = m1[i];
-    for (int i = env.tid; i < 4 * 5; i += env.nthreads) tb->tw400_s2[i] = m2[i];
-    for (int i = env.tid; i < kNfftM; i += env.nthreads) tb->win400[i] = g->win400[i];
-    for (int i = env.tid; i < kNfftP; i += env.nthreads) tb->win512[i] = g->win512[i];
-    for (int i = env.tid; i < kMelNnzMax; i += env.nthreads) {
-      tb->mel_w[i] = g->mel_w[i];
-      tb->mel_pos[2 * i] = g->mel_pos[2 * i];
-      tb->mel_pos[2 * i + 1] = g->mel_pos[2 * i + 1];
-    }
-    for (int i = env.tid; i <= kMels; i += env.nthreads) tb->mel_ptr[i] = g->mel_ptr[i];
-    for (int i = env.tid; i < 2 * 3 * kHopP; i += env.nthreads) carry[i] = 0.0f;
-  }
-  if (has) {
-    const InT* src = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T + lo;
-    env.template load_slice<InT>(wave, src, hi - lo, smem + lay.bar_off, (P.flags & kFlagBulkCopy) != 0);
-  }
+  // ---------------------------------------------------------------- stage the constant tables
+  env.copy16(smem + lay.tab_off, &P.tab->s, (int)sizeof(SmemTables));
+  if (env.warp == 0) env.lanes([&](int lane, int li) { (void)li; if (lane < 4) ctr[lane] = 0; });
   env.sync();
 
   // ---------------------------------------------------------------- K1: energy atoms, totals
-  double e_total = 0.0, e_noise = 0.0;
+  // groups of 640 samples (8 atoms of 80): lane l loads float4 j at sample 128 j + 4 l, a 160-entry
+  // shared-memory tile turns the per-lane partial sums into per-atom sums (20 entries each)
   int n_atoms_local = 0;
-  if (has && (P.parts & kPartWave)) {
-    const int full_end = T - T % kAtom;
-    const int a0 = t0 / kAtom;
-    const int a1 = ((t1 < full_end) ? t1 : full_end) / kAtom;
-    n_atoms_local = (a1 > a0) ? a1 - a0 : 0;
-    for (int a = a0 + env.warp; a < a1; a += env.nwarps) {
-      float s = 0.0f;
-      for (int i = env.lane; i < kAtom; i += LANES) { float x = wave[a * kAtom + i - lo]; s = fmaf(x, x, s); }
-      double sd = env.wsum((double)s);
-      if (env.lane == 0) atoms[a - a0] = (float)sd;
-    }
-    const int nn = P.noise_n;
-    for (int t = t0 + env.tid; t < t1; t += env.nthreads) {
-      double x = wave[t - lo];
-      double x2 = x * x;
-      e_total += x2;
-      if (t < nn || t >= T - nn) e_noise += x2;
-    }
-  }
-  e_total = env.bsum(e_total, red);
-  e_noise = env.bsum(e_noise, red);
-
-  // ---------------------------------------------------------------- K2 phase A: STFT-400 -> power -> mel -> dB
-  const int nFm = T / kHopM + 1;
-  int fm_begin = 0, fm_end = 0;
-  if (has) {
-    fm_begin = ceil_div(t0, kHopM);
-    fm_end = (t1 == T) ? nFm : ceil_div(t1, kHopM);
-  }
-  const int nfr = (P.parts & kPartMfcc) ? (fm_end - fm_begin) : 0;
-  float dbmax = -3.0e38f;
   {
-    c32* zb = zb_all + env.warp * kPad512;
-    const int npairs = (nfr + 1) / 2;
-    for (int pp = env.warp; pp < npairs; pp += env.nwarps) {
-      const int fa = fm_begin + 2 * pp;
-      const bool hasb = (2 * pp + 1) < nfr;
-      const int ca = fa * kHopM - kNfftM / 2, cb = ca + kHopM;
-      if (ca >= 0 && cb + kNfftM <= T) {                 // interior pair: no reflection (warp-uniform branch)
-        const float* wa = wave + (ca - lo);
-        for (int n = env.lane; n < kNfftM; n += LANES) {
-          const float w = tb->win400[n];
-          zb[n] = c32{w * wa[n], hasb ? w * wa[n + kHopM] : 0.0f};
-        }
-      } else {
-        for (int n = env.lane; n < kNfftM; n += LANES) {
-          const float w = tb->win400[n];
-          zb[n] = c32{w * W(ca + n), hasb ? w * W(cb + n) : 0.0f};
-        }
+    double e_tot[S], e_noi[S];
+    for (int i = 0; i < S; ++i) e_tot[i] = e_noi[i] = 0.0;
+    if (P.parts & kPartWave) {
+      const int nG = ceil_div(T, kGroup);
+      const int gper = ceil_div(nG, NR);
+      const int g0 = (r * gper < nG) ? r * gper : nG;
+      const int g1 = (g0 + gper < nG) ? g0 + gper : nG;
+      const int full_atoms = T / kAtom;
+      const int a_lo = g0 * 8;
+      const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
+      n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
+      float* scr = reinterpret_cast<float*>(wbuf);
+      for (int g = g0 + env.warp; g < g1; g += NW) {
+        const int base = g * kGroup;
+        env.lanes([&](int lane, int li) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            float v[4];
+            env.ld4(x, base + 128 * j + 4 * lane, T, v);
+            const float s = fmaf(v[3], v[3], fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0])));
+            scr[32 * j + lane] = s;
+            acc += s;
+          }
+          e_tot[li] += (double)acc;
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          if (lane < 8) {
+            const int a = g * 8 + lane;
+            if (a < full_atoms) {
+              float s = 0.0f;
+#pragma unroll
+              for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
+              atoms[a - a_lo] = s;
+            }
+          }
+        });
+        env.wsync();
       }
-      env.wsync();
-      fft_stage<kNfftM, 16, 400, false, PadNone, LANES>(zb, tb->tw400_s1, env.lane);
-      env.wsync();
-      fft_stage<kNfftM, 5, 25, false, PadNone, LANES>(zb, tb->tw400_s2, env.lane);
-      env.wsync();
-      fft_stage<kNfftM, 5, 5, false, PadNone, LANES>(zb, nullptr, env.lane);
-      env.wsync();
-      // mel energies straight from the packed spectrum: with Z = FFT(a + i b),
-      //   |A_k|^2 = |Z_k + conj Z_{N-k}|^2 / 4,  |B_k|^2 = |Z_k - conj Z_{N-k}|^2 / 4
-      for (int m = env.lane; m < kMels; m += LANES) {
-        const int p0 = tb->mel_ptr[m], p1 = tb->mel_ptr[m + 1];
-        float ea = 0.0f, eb = 0.0f;
-        for (int p = p0; p < p1; ++p) {
-          const c32 zk = zb[tb->mel_pos[2 * p]];
-          const c32 zn = zb[tb->mel_pos[2 * p + 1]];
-          const float w = 0.25f * tb->mel_w[p];
-          const float sx = zk.x + zn.x, sy = zk.y - zn.y;
-          const float dx = zk.x - zn.x, dy = zk.y + zn.y;
-          ea = fmaf(w, fmaf(sx, sx, sy * sy), ea);
-          eb = fmaf(w, fmaf(dx, dx, dy * dy), eb);
+      // noise power: first and last int(0.05 T) samples (audio_analyzer.py:282-285), split over the ranks
+      const int nn = P.noise_n;
+      const int per = ceil_div(2 * nn, NR);
+      const int i0 = (r * per < 2 * nn) ? r * per : 2 * nn;
+      const int i1 = (i0 + per < 2 * nn) ? i0 + per : 2 * nn;
+      env.lanes([&](int lane, int li) {
+        float acc = 0.0f;
+        for (int i = i0 + env.warp * 32 + lane; i < i1; i += env.nthreads) {
+          const float v = env.ld(x + ((i < nn) ? i : T - 2 * nn + i));
+          acc = fmaf(v, v, acc);
         }
-        const float da = 10.0f * log10f(fmaxf(ea, 1e-10f));
-        dbs[(2 * pp) * kDbStride + m] = da;
-        dbmax = fmaxf(dbmax, da);
-        if (hasb) {
-          const float db = 10.0f * log10f(fmaxf(eb, 1e-10f));
-          dbs[(2 * pp + 1) * kDbStride + m] = db;
-          dbmax = fmaxf(dbmax, db);
-        }
-      }
-      env.wsync();
+        e_noi[li] = (double)acc;
+      });
     }
+    env.sync();                                           // the reduction scratch aliases every warp's tiles
+    const int ops[2] = {kOpSum, kOpSum};
+    block_reduce<2>(env, red, rout, ops, [&](int li, int k) { return k == 0 ? e_tot[li] : e_noi[li]; });
+    if (env.tid == 0) { part->e_total = rout[0]; part->e_noise = rout[1]; part->n_atoms = n_atoms_local; }
   }
 
   // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual
-  double p_n = 0.0, p_sum = 0.0, p_sumsq = 0.0;
-  float p_max = 0.0f;
-  if (P.parts & kPartPitch) {
-    const int nFp = T / kHopP + 1;
-    // samples [t0,t1) sit at padded positions [t0+256, t1+256); position tp is covered by frames tp/128-3 .. tp/128
-    const bool any = has;
-    const int pf_lo = ((t0 + kNfftP / 2) >> 7) - 3;
-    const int pf_hi = (t1 + kNfftP / 2 - 1) >> 7;
-    const int pf_begin = (pf_lo > 0) ? pf_lo : 0;
-    const int pf_end = (pf_hi < nFp - 1) ? pf_hi : nFp - 1;             // inclusive
-    const int FB = 2 * env.nwarps;
-    const float inv_n = 1.0f / (float)kNfftP;
-    float* cin = carry;
-    float* cout = carry + 3 * kHopP;
-    c32* zb = zb_all + env.warp * kPad512;
-    for (int fb0 = pf_begin; any && fb0 <= pf_end; fb0 += FB) {
-      const int fa = fb0 + 2 * env.warp;
-      if (fa <= pf_end) {
-        const bool hasb = fa + 1 <= pf_end;
-        const int sa = fa * kHopP - kNfftP / 2, sb = sa + kHopP;
-        if (sa >= 0 && sb + kNfftP <= T) {
-          const float* wa = wave + (sa - lo);
-          for (int n = env.lane; n < kNfftP; n += LANES) {
-            const float w = tb->win512[n];
-            zb[Pad8::at(n)] = c32{w * wa[n], hasb ? w * wa[n + kHopP] : 0.0f};
-          }
-        } else {
-          for (int n = env.lane; n < kNfftP; n += LANES) {
-            const float w = tb->win512[n];
-            zb[Pad8::at(n)] = c32{w * W(sa + n), hasb ? w * W(sb + n) : 0.0f};
-          }
-        }
-        env.wsync();
-        fft_stage<kNfftP, 8, 512, false, Pad8, LANES>(zb, tb->tw512_s1, env.lane);
-        env.wsync();
-        fft_stage<kNfftP, 8, 64, false, Pad8, LANES>(zb, tb->tw512_s2, env.lane);
-        env.wsync();
-        fft_stage<kNfftP, 8, 8, false, Pad8, LANES>(zb, nullptr, env.lane);
-        env.wsync();
-        // phase_vocoder(rate = 1.0) returns its input: the spectrum goes straight back
-        fft_stage<kNfftP, 8, 8, true, Pad8, LANES>(zb, nullptr, env.lane);
-        env.wsync();
-        fft_stage<kNfftP, 8, 64, true, Pad8, LANES>(zb, tb->tw512_s2, env.lane);
-        env.wsync();
-        fft_stage<kNfftP, 8, 512, true, Pad8, LANES>(zb, tb->tw512_s1, env.lane);
-      }
-      env.sync();
-      // overlap-add by gathering: every padded position sums the <= 4 frames of this batch that cover it
-      const int f_hi = (fb0 + FB - 1 < pf_end) ? fb0 + FB - 1 : pf_end;
-      for (int i = env.tid; i < (FB + 3) * kHopP; i += env.nthreads) {
-        const int tp = fb0 * kHopP + i;                 // position in the reflect-padded signal
-        const int fq = tp >> 7, nq = tp & (kHopP - 1);
-        float s = (i < 3 * kHopP) ? cin[i] : 0.0f;
-#pragma unroll
-        for (int j = 3; j >= 0; --j) {
-          const int f = fq - j;
-          if (f >= fb0 && f <= f_hi) {
-            const int n = nq + j * kHopP;
-            const c32 z = zb_all[((f - fb0) >> 1) * kPad512 + Pad8::at(n)];
-            s = fmaf(tb->win512[n] * inv_n, ((f - fb0) & 1) ? z.y : z.x, s);
-          }
-        }
-        if (i < FB * kHopP) {
-          const int t = tp - kNfftP / 2;
-          if (t >= t0 && t < t1) {
-            float env_w = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int f = fq - j;
-              if (f >= 0 && f < nFp) { const float w = tb->win512[nq + j * kHopP]; env_w = fmaf(w, w, env_w); }
-            }
-            const float xh = s / env_w;
-            const float pv = fabsf(wave[t - lo] - xh);
-            p_n += 1.0; p_sum += (double)pv; p_sumsq += (double)pv * (double)pv;
-            p_max = fmaxf(p_max, pv);
-          }
-        } else {
-          cout[i - FB * kHopP] = s;
-        }
-      }
-      env.sync();
-      float* tmp = cin; cin = cout; cout = tmp;
-    }
-  }
-  p_n = env.bsum(p_n, red);
-  p_sum = env.bsum(p_sum, red);
-  p_sumsq = env.bsum(p_sumsq, red);
-  p_max = env.bmax(p_max, red);
-  dbmax = env.bmax(dbmax, red);
-
-  if (env.tid == 0) {
-    part->db_max = dbmax; part->p_max = p_max;
-    part->p_n = p_n; part->p_sum = p_sum; part->p_sumsq = p_sumsq;
-    part->e_total = e_total; part->e_noise = e_noise;
-    part->mf_frames = nfr; part->n_atoms = n_atoms_local;
-  }
-  env.csync();                                            // #1: every rank's dB maximum is visible
-
-  float gmax = -3.0e38f;
-  for (int rr = 0; rr < env.nranks; ++rr) gmax = fmaxf(gmax, env.remote(part, rr)->db_max);
-
-  // ---------------------------------------------------------------- K2 phase B: top_db clamp -> DCT -> moments
   {
-    const float thr = gmax - 80.0f;
-    const float* dct = P.tab->dct;
-    // one thread per (frame, group of 4 coefficients): 13 = 4 + 4 + 4 + 1
-    for (int it = env.tid; it < nfr * 4; it += env.nthreads) {
-      const int fl = it >> 2, kg = it & 3;
-      const float* row = dbs + fl * kDbStride;
-      const float* dk = dct + kg * 4;
-      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-      for (int m = 0; m < kMels; ++m) {
-        const float v = fmaxf(row[m], thr);
-        const float* d = dk + m * kDctStride;
-        a0 = fmaf(v, d[0], a0);
-        a1 = fmaf(v, d[1], a1);                         // columns 13..15 of the padded table are zero
-        a2 = fmaf(v, d[2], a2);
-        a3 = fmaf(v, d[3], a3);
+    double ps[S], pq[S], pn[S];
+    float pmax[S];
+    for (int i = 0; i < S; ++i) { ps[i] = pq[i] = pn[i] = 0.0; pmax[i] = 0.0f; }
+    if (P.parts & kPartPitch) {
+      const int nFp = T / kHopP + 1;
+      // hop-blocks that hold output samples: torch.istft keeps padded positions [256, 256 + T); the last
+      // of them can lie one block past the last frame's first block, so quads cover max(frames, blocks)
+      const int nBl = (T - 1 + kNfftP / 2) / kHopP + 1;
+      const int nQ = ceil_div(nFp > nBl ? nFp : nBl, 4);
+      const int qper = ceil_div(nQ, NR);
+      const int q_begin = (r * qper < nQ) ? r * qper : nQ;
+      const int q_end = (q_begin + qper < nQ) ? q_begin + qper : nQ;
+      const int q_first = (q_begin > 0) ? q_begin - 1 : 0;      // warm-up quad: only its tail is used
+      const int ntasks = (q_end > q_begin) ? q_end - q_first : 0;
+      const int niter = ceil_div(ntasks, NW);
+      float own[S][7][4];
+      for (int it = 0; it < niter; ++it) {
+        const int task = it * NW + env.warp;
+        const bool active = task < ntasks;
+        const int quad = q_first + task;
+        const int f0 = 4 * quad;
+        const int s0 = kHopP * f0 - kNfftP / 2;                  // first sample of frame f0
+        if (active) {
+          const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
+          // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples
+          for (int h = 0; h < 2; ++h) {
+            env.lanes([&](int lane, int li) {
+              (void)li;
+              const int sb = s0 + 2 * h * kHopP;
+              const bool oka = (f0 + 2 * h) < nFp, okb = (f0 + 2 * h + 1) < nFp;
+              float raw[20];
+              if (interior) {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) raw[i] = env.ld(x + sb + 32 * i + lane);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) raw[i] = xr(sb + 32 * i + lane);
+              }
+              c32 z[16];
+#pragma unroll
+              for (int n1 = 0; n1 < 16; ++n1) {
+                const float w = tb->win512[32 * n1 + lane];
+                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
+              }
+              pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
+            });
+          }
+          env.wsync();
+          // pass B forward = the STFT spectrum X[k1 + 16 k2] of this row; phase_vocoder(rate = 1.0)
+          // returns its input, so the inverse radix-32 follows in the same registers
+          env.lanes([&](int lane, int li) {
+            (void)li;
+            c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow512;
+            c32 v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = row[i];
+            dft32<false>(v);
+            dft32<true>(v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) row[i] = v[i];
+          });
+          env.wsync();
+          // inverse pass A, synthesis window (x 1/512), overlap-add of the quad's 4 frames in registers:
+          // frame f0 + j covers hop-blocks j .. j+3 of the quad's 7 blocks
+          env.lanes([&](int lane, int li) {
+#pragma unroll
+            for (int b = 0; b < 7; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) own[li][b][i] = 0.0f;
+          });
+          for (int h = 0; h < 2; ++h) {
+            env.lanes([&](int lane, int li) {
+              c32 z[16];
+              pass_a_inv<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
+              static_for<0, 16>([&](auto nc) {
+                constexpr int n1 = decltype(nc)::value;
+                const float w = tb->win512s[32 * n1 + lane];
+                if (h == 0) {
+                  own[li][n1 / 4][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4][n1 % 4]);
+                  own[li][n1 / 4 + 1][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 1][n1 % 4]);
+                } else {
+                  own[li][n1 / 4 + 2][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4 + 2][n1 % 4]);
+                  own[li][n1 / 4 + 3][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 3][n1 % 4]);
+                }
+              });
+            });
+          }
+          // blocks 4..6 overlap the next quad: slot w+1 holds the tail of the quad warp w just did
+          env.lanes([&](int lane, int li) {
+            float* t = tails + (env.warp + 1) * kTailFloats;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) t[b * kHopP + 32 * i + lane] = own[li][4 + b][i];
+          });
+        }
+        env.sync();
+        if (active && quad >= q_begin) {
+          // finalise blocks 0..3 of the quad: add the predecessor's tail, divide by the window envelope,
+          // compare with the input (torch.istft trims the n_fft/2 padding: t = position - 256)
+          const bool has_prev = quad > 0;
+          const float* pt = tails + env.warp * kTailFloats;      // slot 0 = last warp of the previous iteration
+          const int b0 = 4 * quad;
+          const bool fast = (b0 >= 3) && (b0 + 3 <= nFp - 1) && (kHopP * (b0 + 4) - kNfftP / 2 <= T);
+          env.lanes([&](int lane, int li) {
+            float s1 = 0.0f, s2 = 0.0f, mx = 0.0f;
+            int cnt = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int o = 32 * i + lane;
+                const int t = kHopP * (b0 + b) + o - kNfftP / 2;
+                float y = own[li][b][i];
+                if (b < 3 && has_prev) y += pt[b * kHopP + o];
+                if (fast) {
+                  const float pv = fabsf(env.ld(x + t) - y * tb->ienv[o]);
+                  s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
+                } else if (t >= 0 && t < T) {
+                  float e = 0.0f;
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int f = b0 + b - j;
+                    if (f >= 0 && f < nFp) { const float w = tb->win512[j * kHopP + o]; e = fmaf(w, w, e); }
+                  }
+                  const float pv = fabsf(env.ld(x + t) - y / e);
+                  s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
+                }
+              }
+            ps[li] += (double)s1; pq[li] += (double)s2; pn[li] += (double)cnt;
+            pmax[li] = fmaxf(pmax[li], mx);
+          });
+        }
+        env.sync();
+        if (active && env.warp == NW - 1) {
+          env.lanes([&](int lane, int li) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) tails[b * kHopP + 32 * i + lane] = own[li][4 + b][i];
+          });
+        }
       }
-      float* o = mfcc + fl * kMfcc + kg * 4;
-      o[0] = a0;
-      if (kg < 3) { o[1] = a1; o[2] = a2; o[3] = a3; }
+      env.sync();
+    }
+    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
+    block_reduce<4>(env, red, rout, ops, [&](int li, int k) {
+      return k == 0 ? ps[li] : (k == 1 ? pq[li] : (k == 2 ? pn[li] : (double)pmax[li]));
+    });
+    if (env.tid == 0) { part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3]; }
+  }
+
+  // ---------------------------------------------------------------- K2: STFT-400 -> power -> mel -> dB -> DCT shares
+  const int nFm = T / kHopM + 1;
+  const int nQm = ceil_div(nFm, 4);
+  const int mper = ceil_div(nQm, NR);
+  const int mq_begin = (r * mper < nQm) ? r * mper : nQm;
+  const int mq_end = (mq_begin + mper < nQm) ? mq_begin + mper : nQm;
+  const int mf_begin = 4 * mq_begin;
+  const int mf_end = (4 * mq_end < nFm) ? 4 * mq_end : nFm;
+  const int nfr = ((P.parts & kPartMfcc) && mf_end > mf_begin) ? mf_end - mf_begin : 0;
+
+  // One MFCC pass over this rank's quads.  thr = -inf in the first pass (no clamp on live filters).
+  auto mfcc_pass = [&](float thr, int* counter, float* dbmax_out, float* dbmin_out) {
+    float dmax[S], dmin[S];
+    for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
+    float pw[S][28];
+    float share[S][52];
+    float* fbuf = reinterpret_cast<float*>(wbuf);
+    const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
+    for (;;) {
+      const int task = env.next_task(counter);
+      if (task >= ntasks) break;
+      const int m0 = 4 * (mq_begin + task);
+      const int s0 = kHopM * m0 - kNfftM / 2;
+      const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);
+      for (int h = 0; h < 2; ++h) {
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          if (lane < 25) {
+            const int sb = s0 + 2 * h * kHopM;
+            const bool oka = (m0 + 2 * h) < nFm, okb = (m0 + 2 * h + 1) < nFm;
+            float raw[24];
+            if (interior) {
+#pragma unroll
+              for (int i = 0; i < 24; ++i) raw[i] = env.ld(x + sb + 25 * i + lane);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 24; ++i) raw[i] = xr(sb + 25 * i + lane);
+            }
+            c32 z[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+              const float w = tb->win400[25 * n1 + lane];
+              z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
+            }
+            pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kFftHalf);
+          }
+        });
+      }
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+        (void)li;
+        c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow400;
+        c32 v[25];
+#pragma unroll
+        for (int i = 0; i < 25; ++i) v[i] = row[i];
+        dft25<false>(v);
+#pragma unroll
+        for (int i = 0; i < 25; ++i) row[i] = v[i];                // row[k2] = Z[k1 + 16 k2]
+      });
+      env.wsync();
+      // power of both packed frames: with Z = FFT(a + i b),
+      //   |A_k|^2 = |Z_k + conj Z_{N-k}|^2 / 4,  |B_k|^2 = |Z_k - conj Z_{N-k}|^2 / 4
+      env.lanes([&](int lane, int li) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const c32* zt = wbuf + h * kFftHalf;
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k = lane + 32 * i;
+            float pa = 0.0f, pb = 0.0f;
+            if (k < kBinsM) {
+              const int kk = (k == 0) ? 0 : kNfftM - k;
+              const c32 zk = zt[(k & 15) * kRow400 + (k >> 4)];
+              const c32 zn = zt[(kk & 15) * kRow400 + (kk >> 4)];
+              const float sx = zk.x + zn.x, sy = zk.y - zn.y;
+              const float dx = zk.x - zn.x, dy = zk.y + zn.y;
+              pa = 0.25f * fmaf(sx, sx, sy * sy);
+              pb = 0.25f * fmaf(dx, dx, dy * dy);
+            }
+            pw[li][14 * h + 2 * i] = pa;
+            pw[li][14 * h + 2 * i + 1] = pb;
+          }
+        }
+      });
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float* pr = fbuf + h * (2 * kFftHalf);                    // same bytes as tile h, as floats
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int k = lane + 32 * i;
+            if (k < kPowStride) {                                  // bins 201..207 are written as zeros
+              pr[k] = pw[li][14 * h + 2 * i];
+              pr[kPowStride + k] = pw[li][14 * h + 2 * i + 1];
+            }
+          }
+        }
+      });
+      env.wsync();
+      // mel energies of the lane's 4 filters for the 4 frames, dB, DCT shares
+      env.lanes([&](int lane, int li) {
+        float db[4][4];                                            // [frame][slot]
+        static_for<0, 4>([&](auto sc) {
+          constexpr int s = decltype(sc)::value;
+          constexpr int trips = (s == 0) ? kMelTrip0 : (s == 1) ? kMelTrip1 : (s == 2) ? kMelTrip2 : kMelTrip3;
+          constexpr int toff = (s == 0) ? 0 : (s == 1) ? kMelTrip0 : (s == 2) ? kMelTrip0 + kMelTrip1 : kMelTrip0 + kMelTrip1 + kMelTrip2;
+          const int lo = tb->mel_lo[32 * s + lane];
+          const bool dead = tb->mel_dead[32 * s + lane] != 0;
+          float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
+#pragma unroll
+          for (int p = 0; p < trips; ++p) {
+            const float w = tb->mel_w[(toff + p) * 32 + lane];
+            e0 = fmaf(w, fbuf[lo + p], e0);
+            e1 = fmaf(w, fbuf[kPowStride + lo + p], e1);
+            e2 = fmaf(w, fbuf[2 * kFftHalf + lo + p], e2);
+            e3 = fmaf(w, fbuf[2 * kFftHalf + kPowStride + lo + p], e3);
+          }
+          const float e[4] = {e0, e1, e2, e3};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d = 3.0102999566398120f * env.log2(fmaxf(e[j], 1e-10f));   // 10 log10(max(x, amin))
+            if (!dead && (m0 + j) < nFm) {
+              dmax[li] = fmaxf(dmax[li], d);
+              dmin[li] = fminf(dmin[li], d);
+              d = fmaxf(d, thr);
+            }
+            db[j][s] = d;
+          }
+        });
+#pragma unroll
+        for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
+        const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
+        static_for<0, kDctQuads>([&](auto ic) {
+          constexpr int i = decltype(ic)::value;
+          const float4 q = dq[i * 32 + lane];
+          const float qc[4] = {q.x, q.y, q.z, q.w};
+          static_for<0, 4>([&](auto cc) {
+            constexpr int c = decltype(cc)::value;
+            constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(db[j][s], qc[c], share[li][j * kMfcc + k]);
+          });
+        });
+      });
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+#pragma unroll
+        for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
+      });
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+        (void)li;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int v = lane + 32 * half;
+          if (v < 52) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a += fbuf[v * 33 + j];
+            const int fr = m0 + v / kMfcc;
+            if (fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = a;
+          }
+        }
+      });
+      env.wsync();
     }
     env.sync();
-    if (P.dbg_mfcc) {
-      float* o = P.dbg_mfcc + ((size_t)seg * nFm + fm_begin) * kMfcc;
-      for (int i = env.tid; i < nfr * kMfcc; i += env.nthreads) o[i] = mfcc[i];
+    const int ops[2] = {kOpMax, kOpMin};
+    block_reduce<2>(env, red, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
+    *dbmax_out = (float)rout[0];
+    *dbmin_out = (float)rout[1];
+    env.sync();
+  };
+
+  float dbmax = -3.0e38f, dbmin = 3.0e38f;
+  mfcc_pass(-3.0e38f, ctr, &dbmax, &dbmin);
+  if (env.tid == 0) { part->db_max = dbmax; part->db_min = dbmin; part->mf_frames = nfr; }
+  env.csync();                                            // #1: every rank's dB extrema are visible
+
+  float gmax = -3.0e38f, gmin = 3.0e38f;
+  for (int rr = 0; rr < NR; ++rr) {
+    const Partials* rp = env.remote(part, rr);
+    gmax = fmaxf(gmax, rp->db_max);
+    gmin = fminf(gmin, rp->db_min);
+  }
+  // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  Live filters below it are rare: redo the pass clamped.
+  const float thr = gmax - 80.0f;
+  const bool slow = (P.parts & kPartMfcc) && (gmin < thr);
+  if (slow) {
+    float a, b;
+    mfcc_pass(thr, ctr + 1, &a, &b);
+  }
+
+  // ---------------------------------------------------------------- MFCC moments (timbre z-score, clarity)
+  {
+    const float cdead = fmaxf(-100.0f, thr);              // every frame of an empty mel filter sits at this level
+    double acc[S][16];
+    for (int i = 0; i < S; ++i)
+      for (int k = 0; k < 16; ++k) acc[i][k] = 0.0;
+    env.lanes([&](int lane, int li) {
+      for (int fl = env.warp * 32 + lane; fl < nfr; fl += env.nthreads) {
+        float* o = P.dbg_mfcc ? P.dbg_mfcc + ((size_t)seg * nFm + mf_begin + fl) * kMfcc : nullptr;
+#pragma unroll
+        for (int k = 0; k < kMfcc; ++k) {
+          const float vf = fmaf(cdead, tb->dct_dead[k], mfl[fl * kMfcc + k]);
+          if (o) o[k] = vf;
+          const double v = vf;
+          acc[li][k] += v;
+          acc[li][13] += v * v;
+          if (k < 6) acc[li][14] += fabs(v); else acc[li][15] += fabs(v);
+        }
+      }
+    });
+    const int ops[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    block_reduce<16>(env, red, rout, ops, [&](int li, int k) { return acc[li][k]; });
+    if (env.tid == 0) {
+      for (int k = 0; k < kMfcc; ++k) part->mf_sum[k] = rout[k];
+      part->mf_sumsq = rout[13]; part->mf_abs_lo = rout[14]; part->mf_abs_hi = rout[15];
+      part->slow_pass = slow ? 1 : 0;
     }
-    double ss = 0.0, alo = 0.0, ahi = 0.0;
-    for (int i = env.tid; i < nfr * kMfcc; i += env.nthreads) {
-      const double v = mfcc[i];
-      ss += v * v;
-      if (i % kMfcc < 6) alo += fabs(v); else ahi += fabs(v);
-    }
-    ss = env.bsum(ss, red); alo = env.bsum(alo, red); ahi = env.bsum(ahi, red);
-    // per-coefficient time sums: warp w reduces coefficient k = w, w + nwarps, ...
-    for (int k = env.warp; k < kMfcc; k += env.nwarps) {
-      double sk = 0.0;
-      for (int fl = env.lane; fl < nfr; fl += LANES) sk += (double)mfcc[fl * kMfcc + k];
-      sk = env.wsum(sk);
-      if (env.lane == 0) part->mf_sum[k] = sk;
-    }
-    if (env.tid == 0) { part->mf_sumsq = ss; part->mf_abs_lo = alo; part->mf_abs_hi = ahi; }
   }
   env.csync();                                            // #2: all partial moments and atoms are visible
 
   // ---------------------------------------------------------------- rank 0: merge and assemble the row
   if (r == 0) {
-    // gather the energy atoms of all ranks (re-using the FFT buffers, idle by now)
-    float* all_atoms = reinterpret_cast<float*>(zb_all);
-    const int atoms_cap = env.nwarps * kPad512 * 2;
+    // gather the energy atoms of all ranks (re-using the FFT tiles, idle by now)
+    float* all_atoms = reinterpret_cast<float*>(smem + lay.buf_off);
     int nA = 0;
-    for (int rr = 0; rr < env.nranks; ++rr) {
+    for (int rr = 0; rr < NR; ++rr) {
       const Partials* rp = env.remote(part, rr);
       const float* ra = env.remote(atoms, rr);
       const int n = rp->n_atoms;
-      for (int i = env.tid; i < n && nA + i < atoms_cap; i += env.nthreads) all_atoms[nA + i] = ra[i];
+      env.lanes([&](int lane, int li) {
+        (void)li;
+        for (int i = env.warp * 32 + lane; i < n; i += env.nthreads) all_atoms[nA + i] = ra[i];
+      });
       nA += n;
     }
     env.sync();
     // rhythm: frame energies e_g = sum of 5 atoms at stride 2 (400 = 5*80, 160 = 2*80)
-    const int nG = (T >= kRhythmWin) ? (T - kRhythmWin) / kRhythmHop + 1 : 0;
-    double gs = 0.0;
-    for (int g = env.tid; g < nG; g += env.nthreads) {
-      const float* a = all_atoms + 2 * g;
-      gs += (double)(a[0] + a[1] + a[2] + a[3] + a[4]);
-    }
-    gs = env.bsum(gs, red);
-    const double gmean = (nG > 0) ? gs / nG : 0.0;
-    double gq = 0.0;
-    for (int g = env.tid; g < nG; g += env.nthreads) {
-      const float* a = all_atoms + 2 * g;
-      const double d = (double)(a[0] + a[1] + a[2] + a[3] + a[4]) - gmean;
-      gq += d * d;
-    }
-    gq = env.bsum(gq, red);
-    // consistency: 1600-sample block mean-squares = 20 atoms / 1600
-    const int nBk = T / kBlock;
-    double bs = 0.0;
-    for (int b = env.tid; b < nBk; b += env.nthreads) {
-      float acc = 0.0f;
-      for (int j = 0; j < 20; ++j) acc += all_atoms[20 * b + j];
-      bs += (double)(acc * (1.0f / (float)kBlock));
-    }
-    bs = env.bsum(bs, red);
-    const double bmean = (nBk > 0) ? bs / nBk : 0.0;
-    double bq = 0.0;
-    for (int b = env.tid; b < nBk; b += env.nthreads) {
-      float acc = 0.0f;
-      for (int j = 0; j < 20; ++j) acc += all_atoms[20 * b + j];
-      const double d = (double)(acc * (1.0f / (float)kBlock)) - bmean;
-      bq += d * d;
-    }
-    bq = env.bsum(bq, red);
+    const int nG = (T >= kRhythmWin && (P.parts & kPartWave)) ? (T - kRhythmWin) / kRhythmHop + 1 : 0;
+    const int nBk = (P.parts & kPartWave) ? T / kBlock : 0;
+    auto frame_e = [&](int g) { const float* a = all_atoms + 2 * g; return (double)(a[0] + a[1] + a[2] + a[3] + a[4]); };
+    auto block_ms = [&](int b) {
+      float s = 0.0f;
+      for (int j = 0; j < 20; ++j) s += all_atoms[20 * b + j];
+      return (double)(s * (1.0f / (float)kBlock));
+    };
+    // the means and centred sums of squares are tiny (498 frames, 50 blocks): every thread of warp 0 .. NW-1
+    // accumulates a strided share, two deterministic block reductions finish them
+    double gs[S], bs[S];
+    env.lanes([&](int lane, int li) {
+      double a = 0.0, b = 0.0;
+      for (int g = env.warp * 32 + lane; g < nG; g += env.nthreads) a += frame_e(g);
+      for (int k = env.warp * 32 + lane; k < nBk; k += env.nthreads) b += block_ms(k);
+      gs[li] = a; bs[li] = b;
+    });
+    const int ops2[2] = {kOpSum, kOpSum};
+    // the atoms live where the reduction scratch is: reduce through the tail tiles instead
+    double* red2 = reinterpret_cast<double*>(smem + lay.tail_off);
+    block_reduce<2>(env, red2, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
+    const double gmean = (nG > 0) ? rout[0] / nG : 0.0;
+    const double bmean = (nBk > 0) ? rout[1] / nBk : 0.0;
+    env.sync();
+    env.lanes([&](int lane, int li) {
+      double a = 0.0, b = 0.0;
+      for (int g = env.warp * 32 + lane; g < nG; g += env.nthreads) { const double d = frame_e(g) - gmean; a += d * d; }
+      for (int k = env.warp * 32 + lane; k < nBk; k += env.nthreads) { const double d = block_ms(k) - bmean; b += d * d; }
+      gs[li] = a; bs[li] = b;
+    });
+    block_reduce<2>(env, red2, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
+    const double gq = rout[0], bq = rout[1];
 
     if (env.tid == 0) {
       const double NaN = nan("");
       Partials tot = *part;
-      for (int rr = 1; rr < env.nranks; ++rr) {
+      for (int rr = 1; rr < NR; ++rr) {
         const Partials* rp = env.remote(part, rr);
         for (int k = 0; k < kMfcc; ++k) tot.mf_sum[k] += rp->mf_sum[k];
         tot.mf_sumsq += rp->mf_sumsq; tot.mf_abs_lo += rp->mf_abs_lo; tot.mf_abs_hi += rp->mf_abs_hi;
@@ -521,7 +764,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       }
       // quality scalars (python floats in the reference: double arithmetic on fp32 .item() values)
       double snr = 0.0, consistency = 0.0;
-      if (P.noise_n > 0) {
+      if (P.noise_n > 0 && (P.parts & kPartWave)) {
         const float noise_p = (float)(tot.e_noise / (2.0 * P.noise_n));
         const float sig_p = (float)(tot.e_total / (double)T);
         const float snr_db = 10.0f * log10f(sig_p / (noise_p + 1e-6f));
@@ -567,7 +810,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         d[64] = gmax; d[65] = (float)p_mean; d[66] = (float)p_std; d[67] = tot.p_max;
         d[68] = (float)tot.e_total; d[69] = (float)tot.e_noise; d[70] = (float)tot.mf_frames; d[71] = (float)nG;
         d[72] = (float)tot.p_n; d[73] = (float)nBk; d[74] = (float)nA;
-        for (int k = 75; k < kDetailStride; ++k) d[k] = 0.0f;
+        d[75] = slow ? 1.0f : 0.0f; d[76] = gmin;
+        for (int k = 77; k < kDetailStride; ++k) d[k] = 0.0f;
       }
     }
   }

@@ -1,13 +1,17 @@
-// In-place mixed-radix FFTs executed by ONE WARP per transform, data in shared memory.
+// Register-resident DFT butterflies (radix 4, 5, 8, 16, 25, 32) on complex fp32 values.
 //
-// Forward = decimation in frequency (natural order in, digit-reversed out); inverse =
-// the exact stage-by-stage inverse (digit-reversed in, natural out, unnormalised).  The
-// STFT -> ISTFT round trip of the "pitch" feature therefore needs no permutation at all,
-// and the MFCC power spectrum reads its bins through a 400-entry position table.
+// The two transform sizes of the audio path are factored so that every pass runs entirely in
+// registers and a transform crosses shared memory exactly once per direction:
+//     512 = 16 x 32   (STFT of torchaudio.transforms.PitchShift, audio_analyzer.py:43-47)
+//     400 = 16 x 25   (STFT inside torchaudio.transforms.MFCC,   audio_analyzer.py:207-210)
+// With n = N2 n1 + n2 and k = k1 + 16 k2 (N2 = 32 or 25):
+//     X[k1 + 16 k2] = sum_n2 W_N2^(n2 k2) * W_N^(n2 k1) * ( sum_n1 x[N2 n1 + n2] W_16^(n1 k1) )
+// Pass A: lane n2 runs one radix-16 butterfly over the stride-N2 samples it loaded itself and
+// applies the inter-pass twiddle; pass B: lane k1 runs one radix-N2 butterfly on one row.
+// All butterflies take and return NATURAL order (pure register renaming), so there are no
+// digit-reversal tables.  Twiddle factors inside a butterfly are compile-time constants.
 //
-// Compiled both by nvcc (device) and by g++ (tests/emu, CPU emulation of a warp:
-// the lane loop runs sequentially, which is valid because within one stage every
-// butterfly reads and writes only its own R positions).
+// Compiled by nvcc (device) and by g++ (tests/emu, CPU emulation of a warp).
 #pragma once
 #include "msa_hd.h"
 
@@ -20,118 +24,154 @@ MSA_FN c32 cmul(c32 a, c32 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y *
 MSA_FN c32 cmulc(c32 a, c32 b) { return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
 template <bool INV> MSA_FN c32 rot90(c32 a) { return INV ? c32{-a.y, a.x} : c32{a.y, -a.x}; }  // * W4 (fwd: -i)
 
-template <bool INV> MSA_FN void dft2(c32& a, c32& b) { c32 t = a - b; a = a + b; b = t; }
+// cos(pi * j / 16), j = 0..16
+template <int J> MSA_FN constexpr float cospi16() {
+  constexpr float t[17] = {1.0f,
+                           0.98078528040323043058f,
+                           0.92387953251128673848f,
+                           0.83146961230254523567f,
+                           0.70710678118654757274f,
+                           0.55557023301960228867f,
+                           0.38268343236508983729f,
+                           0.19509032201612833135f,
+                           0.0f,
+                           -0.19509032201612833135f,
+                           -0.38268343236508983729f,
+                           -0.55557023301960228867f,
+                           -0.70710678118654757274f,
+                           -0.83146961230254523567f,
+                           -0.92387953251128673848f,
+                           -0.98078528040323043058f,
+                           -1.0f};
+  return t[J];
+}
+template <int J> MSA_FN constexpr float sinpi16() { return J <= 8 ? cospi16<8 - (J <= 8 ? J : 8)>() : cospi16<(J > 8 ? J : 8) - 8>(); }
+
+// cos / sin (2 pi j / 25), j = 0..24
+template <int J> MSA_FN constexpr float cos2pi25() {
+  constexpr float t[13] = {1.0f,
+                           0.96858316112863107605f,
+                           0.87630668004386358394f,
+                           0.72896862742141155245f,
+                           0.53582679497899654564f,
+                           0.30901699437494745126f,
+                           0.06279051952931352654f,
+                           -0.18738131458572460097f,
+                           -0.42577929156507271502f,
+                           -0.63742398974868974548f,
+                           -0.80901699437494734024f,
+                           -0.92977648588825134723f,
+                           -0.99211470131447776488f};
+  return t[J <= 12 ? J : 25 - J];
+}
+template <int J> MSA_FN constexpr float sin2pi25() {
+  constexpr float t[13] = {0.0f,
+                           0.24868988716485479484f,
+                           0.48175367410171532345f,
+                           0.68454710592868861507f,
+                           0.84432792550201507531f,
+                           0.95105651629515353118f,
+                           0.99802672842827155897f,
+                           0.98228725072868872115f,
+                           0.90482705246601946580f,
+                           0.77051324277578925326f,
+                           0.58778525229247324813f,
+                           0.36812455268467814129f,
+                           0.12533323356430453588f};
+  return J <= 12 ? t[J <= 12 ? J : 0] : -t[J > 12 ? 25 - J : 0];
+}
+
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1
+template <int I> struct IC { static constexpr int value = I; };
+template <int I, int N, class F> MSA_FN void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(IC<I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// a * W_32^K  (forward: exp(-2 pi i K / 32); inverse: conjugate), K = 0..15
+template <int K, bool INV> MSA_FN c32 mul_w32(c32 a) {
+  if constexpr (K == 0) {
+    return a;
+  } else if constexpr (K == 8) {
+    return rot90<INV>(a);
+  } else if constexpr (K == 4) {
+    constexpr float h = 0.70710678118654752440f;
+    return INV ? c32{(a.x - a.y) * h, (a.x + a.y) * h} : c32{(a.x + a.y) * h, (a.y - a.x) * h};
+  } else if constexpr (K == 12) {
+    constexpr float h = 0.70710678118654752440f;
+    return INV ? c32{(-a.x - a.y) * h, (a.x - a.y) * h} : c32{(a.y - a.x) * h, -(a.x + a.y) * h};
+  } else {
+    constexpr float c = cospi16<K>(), s = sinpi16<K>();        // angle = pi K / 16
+    // forward w = (c, -s): (a.x c + a.y s, a.y c - a.x s); inverse w = (c, s)
+    return INV ? c32{a.x * c - a.y * s, a.y * c + a.x * s} : c32{a.x * c + a.y * s, a.y * c - a.x * s};
+  }
+}
 
 template <bool INV> MSA_FN void dft4(c32& a, c32& b, c32& c, c32& d) {
   c32 t0 = a + c, t1 = a - c, t2 = b + d, t3 = rot90<INV>(b - d);
   a = t0 + t2; b = t1 + t3; c = t0 - t2; d = t1 - t3;
 }
 
-// v[k] <- sum_q v[q] W8^{qk}
-template <bool INV> MSA_FN void dft8(c32* v) {
-  const float h = 0.70710678118654752440f;
-  dft4<INV>(v[0], v[2], v[4], v[6]);   // E0..E3 in v0,v2,v4,v6
-  dft4<INV>(v[1], v[3], v[5], v[7]);   // O0..O3 in v1,v3,v5,v7
-  c32 o1 = v[3], o3 = v[7];
-  c32 w1, w3;
-  if (INV) { w1 = {(o1.x - o1.y) * h, (o1.x + o1.y) * h}; w3 = {(-o3.x - o3.y) * h, (o3.x - o3.y) * h}; }
-  else     { w1 = {(o1.x + o1.y) * h, (o1.y - o1.x) * h}; w3 = {(o3.y - o3.x) * h, -(o3.x + o3.y) * h}; }
-  c32 w0 = v[1], w2 = rot90<INV>(v[5]);
-  c32 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
-  v[0] = e0 + w0; v[4] = e0 - w0;
-  v[1] = e1 + w1; v[5] = e1 - w1;
-  v[2] = e2 + w2; v[6] = e2 - w2;
-  v[3] = e3 + w3; v[7] = e3 - w3;
-}
-
-template <bool INV> MSA_FN void dft16(c32* v) {
-  c32 e[8], o[8];
+// v[k] <- sum_q v[q] W_N^{qk}, radix-2 decimation in time built on dft4 (N = 4, 8, 16, 32)
+template <int N, bool INV> MSA_FN void dft_pow2(c32* v) {
+  if constexpr (N == 4) {
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+  } else {
+    c32 e[N / 2], o[N / 2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
-  dft8<INV>(e);
-  dft8<INV>(o);
-  // W16^k = (cos(pi k/8), -/+ sin(pi k/8))
-  const float c[8] = {1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f,
-                      0.0f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f};
-  const float s[8] = {0.0f, 0.38268343236508977173f, 0.70710678118654752440f, 0.92387953251128675613f,
-                      1.0f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f};
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    c32 w = {c[k], INV ? s[k] : -s[k]};
-    c32 t = cmul(o[k], w);
-    v[k] = e[k] + t;
-    v[k + 8] = e[k] - t;
+    for (int i = 0; i < N / 2; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+    dft_pow2<N / 2, INV>(e);
+    dft_pow2<N / 2, INV>(o);
+    static_for<0, N / 2>([&](auto kc) {
+      constexpr int k = decltype(kc)::value;
+      const c32 t = mul_w32<k*(32 / N), INV>(o[k]);
+      v[k] = e[k] + t;
+      v[k + N / 2] = e[k] - t;
+    });
   }
 }
+template <bool INV> MSA_FN void dft16(c32* v) { dft_pow2<16, INV>(v); }
+template <bool INV> MSA_FN void dft32(c32* v) { dft_pow2<32, INV>(v); }
 
-template <bool INV> MSA_FN void dft5(c32* v) {
-  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
-  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
-  c32 a1 = v[1] + v[4], a2 = v[2] + v[3], d1 = v[1] - v[4], d2 = v[2] - v[3];
-  c32 y0 = {v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y};
-  c32 a = {v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y};
-  c32 b = {v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y};
+template <bool INV> MSA_FN void dft5(c32& v0, c32& v1, c32& v2, c32& v3, c32& v4) {
+  constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
+  constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
+  c32 a1 = v1 + v4, a2 = v2 + v3, d1 = v1 - v4, d2 = v2 - v3;
+  c32 y0 = {v0.x + a1.x + a2.x, v0.y + a1.y + a2.y};
+  c32 a = {v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y};
+  c32 b = {v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y};
   c32 e = {s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y};
   c32 g = {s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y};
   // forward: y1 = a - i e, y4 = a + i e, y2 = b - i g, y3 = b + i g   (inverse: conjugate signs)
-  c32 ie = INV ? c32{-e.y, e.x} : c32{e.y, -e.x};     // (-/+ i) * e  -> fwd: -i e
+  c32 ie = INV ? c32{-e.y, e.x} : c32{e.y, -e.x};
   c32 ig = INV ? c32{-g.y, g.x} : c32{g.y, -g.x};
-  v[0] = y0;
-  v[1] = a + ie; v[4] = a - ie;
-  v[2] = b + ig; v[3] = b - ig;
+  v0 = y0;
+  v1 = a + ie; v4 = a - ie;
+  v2 = b + ig; v3 = b - ig;
 }
 
-template <int R, bool INV> MSA_FN void dftR(c32* v) {
-  if (R == 2) dft2<INV>(v[0], v[1]);
-  else if (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
-  else if (R == 5) dft5<INV>(v);
-  else if (R == 8) dft8<INV>(v);
-  else dft16<INV>(v);
-}
-
-struct PadNone { MSA_FN static int at(int i) { return i; } };
-struct Pad8 { MSA_FN static int at(int i) { return i + (i >> 3); } };   // 512-pt: kills the stride-8 bank conflicts
-constexpr int kPad512 = 512 + 64;
-
-// One radix-R stage over an N-point transform whose current sub-transform size is NS.
-// tw = per-stage twiddle table W_NS^(j*k) stored [k-1][j] as (cos, -sin); unused when m == 1.
-// LANES is the number of lanes sharing the N/R butterflies (32 on the GPU -> fully unrolled, 1 in the
-// CPU emulation); every lane's butterflies are independent, so the compiler can overlap their loads.
-template <int N, int R, int NS, bool INV, class P, int LANES>
-MSA_FN void fft_stage(c32* zb, const c32* tw, int lane) {
-  constexpr int m = NS / R;
-  constexpr int items = N / R;
-  constexpr int per_lane = (items + LANES - 1) / LANES;
+// 25-point DFT, natural order in and out: n = 5a + b, k = c + 5d
+//   X[c + 5d] = sum_b W5^{bd} * ( W25^{bc} * sum_a x[5a + b] W5^{ac} )
+template <bool INV> MSA_FN void dft25(c32* v) {
 #pragma unroll
-  for (int u = 0; u < per_lane; ++u) {
-    const int it = lane + u * LANES;
-    if (items % LANES == 0 || it < items) {
-      const int b = it / m, j = it - b * m;
-      const int base = b * NS + j;
-      c32 v[R];
+  for (int b = 0; b < 5; ++b) dft5<INV>(v[b], v[5 + b], v[10 + b], v[15 + b], v[20 + b]);   // over a -> index c at v[5c + b]
+  static_for<1, 5>([&](auto bc) {
+    static_for<1, 5>([&](auto cc) {
+      constexpr int b = decltype(bc)::value, c = decltype(cc)::value;
+      constexpr float wc = cos2pi25<b * c>(), ws = sin2pi25<b * c>();
+      const c32 a = v[5 * c + b];
+      v[5 * c + b] = INV ? c32{a.x * wc - a.y * ws, a.y * wc + a.x * ws} : c32{a.x * wc + a.y * ws, a.y * wc - a.x * ws};
+    });
+  });
 #pragma unroll
-      for (int q = 0; q < R; ++q) v[q] = zb[P::at(base + q * m)];
-      if (INV) {
-        if (m > 1) {
+  for (int c = 0; c < 5; ++c) dft5<INV>(v[5 * c], v[5 * c + 1], v[5 * c + 2], v[5 * c + 3], v[5 * c + 4]);  // over b -> d at v[5c + d]
+  // v[5c + d] holds X[c + 5d]: transpose the 5x5 register tile to natural order
 #pragma unroll
-          for (int k = 1; k < R; ++k) {
-            v[k] = cmulc(v[k], tw[(k - 1) * m + j]);
-          }
-        }
-        dftR<R, true>(v);
-      } else {
-        dftR<R, false>(v);
-        if (m > 1) {
+  for (int c = 0; c < 5; ++c)
 #pragma unroll
-          for (int k = 1; k < R; ++k) {
-            v[k] = cmul(v[k], tw[(k - 1) * m + j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < R; ++q) zb[P::at(base + q * m)] = v[q];
-    }
-  }
+    for (int d = c + 1; d < 5; ++d) { const c32 t = v[5 * c + d]; v[5 * c + d] = v[5 * d + c]; v[5 * d + c] = t; }
 }
 
 }  // namespace msa

@@ -24,5 +24,5 @@ e0.record()
 for _ in range(10): run()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"threads={os.environ.get('MSA_FEAT_THREADS','dflt')} slice={os.environ.get('MSA_FEAT_SLICE','dflt')} cluster={lib.msa_features_cluster_size(80000)} "
+print(f"threads={os.environ.get('MSA_FEAT_THREADS','dflt')} cluster={lib.msa_features_cluster_size(80000)} "
       f"B={B} {dtype}: {ms:.3f} ms  -> {B*5/ms*1e3/1e6:.2f} M audio-s/s, {320124*B/ms/1e6:.1f} GB/s algorithmic")

@@ -1,19 +1,24 @@
 // CPU emulation of the fused feature kernel (TEST INFRASTRUCTURE).
 //
 // Compiles the SAME kernel body as the CUDA build (csrc/msa_features_body.cuh) with g++ and
-// runs one thread-block cluster per segment on OS threads: one std::thread per WARP (lanes are
-// executed sequentially inside the per-lane loops, nlanes = 1), std::barrier for the block and
-// cluster barriers, and plain pointers for distributed shared memory.  It exists so that the
-// slicing / ownership / overlap-add / digit-reversal logic can be checked against the oracle in
-// a container without a GPU.  It is not a product path and is never loaded by msa_b200.
+// runs one thread-block cluster per segment on OS threads: one std::thread per WARP, whose 32
+// lanes run sequentially inside every lanes() call (per-lane state is kept in 32 copies, warp
+// barriers are therefore no-ops), std::barrier for the block and cluster barriers, and plain
+// pointers for distributed shared memory.  It exists so that the quad / tail / reflect-padding /
+// ownership logic and the register FFTs can be checked against the oracle in a container without
+// a GPU.  It is not a product path and is never loaded by msa_b200.
+#include <atomic>
 #include <barrier>
 #include <cmath>
+#include <complex>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <thread>
 #include <vector>
+
+struct float4 { float x, y, z, w; };
 
 #include "msa_features_body.cuh"
 
@@ -26,39 +31,30 @@ struct CpuCluster {
 };
 
 struct CpuEnv {
-  static constexpr int kLanes = 1;
-  int tid, nthreads, lane, nlanes, warp, nwarps, rank, nranks, cluster_id;
+  static constexpr int kStates = 32;
+  int tid, nthreads, lane, warp, nwarps, rank, nranks, cluster_id;
   std::barrier<>* block;
   CpuCluster* cl;
 
+  template <class F> void lanes(F&& f) {
+    for (int l = 0; l < 32; ++l) f(l, l);
+  }
   void sync() { block->arrive_and_wait(); }
   void wsync() {}
   void csync() { cl->bar.arrive_and_wait(); }
   template <class T> T* remote(T* p, int r) {
     return reinterpret_cast<T*>(cl->smem[r] + (reinterpret_cast<unsigned char*>(p) - cl->smem[rank]));
   }
-  double wsum(double v) { return v; }
-  float wmax(float v) { return v; }
-  double bsum(double v, double* red) {
-    red[tid] = v;
-    sync();
-    double s = 0.0;
-    for (int i = 0; i < nthreads; ++i) s += red[i];
-    sync();
-    return s;
+  float log2(float v) { return std::log2(v); }
+  float ld(const float* p) { return *p; }
+  float ld(const int16_t* p) { return (float)*p * (1.0f / 32768.0f); }
+  template <class InT> void ld4(const InT* x, int idx, int T, float* v) {
+    for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? ld(x + idx + i) : 0.0f;
   }
-  float bmax(float v, double* red) {
-    float* r = reinterpret_cast<float*>(red);
-    r[tid] = v;
-    sync();
-    float s = r[0];
-    for (int i = 1; i < nthreads; ++i) s = std::fmax(s, r[i]);
-    sync();
-    return s;
+  void copy16(void* dst, const void* src, int bytes) {
+    if (warp == 0) std::memcpy(dst, src, bytes);
   }
-  template <class InT> void load_slice(float* dst, const InT* src, int n, void*, bool) {
-    for (int i = tid; i < n; i += nthreads) dst[i] = to_f32<InT>(src[i]);
-  }
+  int next_task(int* ctr) { return __atomic_fetch_add(ctr, 1, __ATOMIC_RELAXED); }
 };
 
 }  // namespace msa
@@ -68,13 +64,16 @@ extern "C" int emu_features(const void* wav, int is_s16, int B, int T, int nrank
   using namespace msa;
   static FeatureTables tab;
   static bool built = false;
-  if (!built) { build_feature_tables(tab); built = true; }
-  int L = (T + nranks - 1) / nranks;
-  L = ((L + kAtom - 1) / kAtom) * kAtom;
+  if (!built) {
+    if (build_feature_tables(tab) != 0) return -100;
+    built = true;
+  }
+  if (T <= kNfftP / 2) parts &= ~kPartPitch;
+  if (T <= kNfftM / 2) parts &= ~kPartMfcc;
   FeatParams P{};
-  P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.slice_len = L; P.noise_n = (int)(0.05 * (double)T);
+  P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.noise_n = (int)(0.05 * (double)T);
   P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.tab = &tab; P.flags = flags; P.parts = parts;
-  const FeatLayout lay = feat_layout(L, nwarps);
+  const FeatLayout lay = feat_layout(T, nranks, nwarps);
   for (int seg = 0; seg < B; ++seg) {
     CpuCluster cl(nranks * nwarps);
     std::vector<std::unique_ptr<unsigned char[]>> mem;
@@ -89,7 +88,7 @@ extern "C" int emu_features(const void* wav, int is_s16, int B, int T, int nrank
     for (int r = 0; r < nranks; ++r)
       for (int w = 0; w < nwarps; ++w)
         th.emplace_back([&, r, w]() {
-          CpuEnv env{w, nwarps, 0, 1, w, nwarps, r, nranks, seg, bars[r].get(), &cl};
+          CpuEnv env{w * 32, nwarps * 32, 0, w, nwarps, r, nranks, seg, bars[r].get(), &cl};
           if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
           else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
         });
@@ -98,8 +97,40 @@ extern "C" int emu_features(const void* wav, int is_s16, int B, int T, int nrank
   return 0;
 }
 
-extern "C" int emu_layout_bytes(int T, int nranks, int nwarps) {
-  int L = (T + nranks - 1) / nranks;
-  L = ((L + msa::kAtom - 1) / msa::kAtom) * msa::kAtom;
-  return msa::feat_layout(L, nwarps).total;
+extern "C" int emu_layout_bytes(int T, int nranks, int nwarps) { return msa::feat_layout(T, nranks, nwarps).total; }
+
+// ---- the register butterflies on their own (checked against numpy.fft in tests/test_emu_features.py)
+extern "C" void emu_dft(int n, int inverse, const float* in, float* out) {
+  using namespace msa;
+  c32 v[32];
+  for (int i = 0; i < n; ++i) v[i] = c32{in[2 * i], in[2 * i + 1]};
+  if (n == 16) { if (inverse) dft16<true>(v); else dft16<false>(v); }
+  else if (n == 32) { if (inverse) dft32<true>(v); else dft32<false>(v); }
+  else if (n == 25) { if (inverse) dft25<true>(v); else dft25<false>(v); }
+  else if (n == 5) { if (inverse) dft5<true>(v[0], v[1], v[2], v[3], v[4]); else dft5<false>(v[0], v[1], v[2], v[3], v[4]); }
+  for (int i = 0; i < n; ++i) { out[2 * i] = v[i].x; out[2 * i + 1] = v[i].y; }
+}
+
+// full two-pass transform of one complex vector of 512 or 400 points through the tile layout
+extern "C" int emu_fft(int n, const float* in, float* out) {
+  using namespace msa;
+  static FeatureTables tab;
+  static bool built = false;
+  if (!built) { if (build_feature_tables(tab) != 0) return -100; built = true; }
+  std::vector<c32> tile(kFftHalf);
+  const int n2 = n / 16;
+  const c32* tw = reinterpret_cast<const c32*>(n == 512 ? tab.s.tw512 : tab.s.tw400);
+  for (int lane = 0; lane < n2; ++lane) {
+    c32 z[16];
+    for (int n1 = 0; n1 < 16; ++n1) z[n1] = c32{in[2 * (n2 * n1 + lane)], in[2 * (n2 * n1 + lane) + 1]};
+    if (n == 512) pass_a_fwd<kRow512>(z, tw, lane, tile.data()); else pass_a_fwd<kRow400>(z, tw, lane, tile.data());
+  }
+  for (int k1 = 0; k1 < 16; ++k1) {
+    c32 v[32];
+    c32* row = tile.data() + k1 * (n == 512 ? kRow512 : kRow400);
+    for (int i = 0; i < n2; ++i) v[i] = row[i];
+    if (n == 512) dft32<false>(v); else dft25<false>(v);
+    for (int k2 = 0; k2 < n2; ++k2) { out[2 * (k1 + 16 * k2)] = v[k2].x; out[2 * (k1 + 16 * k2) + 1] = v[k2].y; }
+  }
+  return 0;
 }

@@ -64,7 +64,7 @@ def check_against_oracle(det, feat, x, emo=None, rel=1e-3, floor=1e-5):
     assert np.all(np.abs(feat - row) <= rel * np.abs(row) + floor)
 
 
-@pytest.mark.parametrize("nranks,nwarps", [(1, 8), (2, 4), (4, 8), (8, 2)])
+@pytest.mark.parametrize("nranks,nwarps", [(1, 8), (2, 4), (4, 8), (8, 2), (1, 16)])
 def test_seeded_segment_all_cluster_sizes(emu, nranks, nwarps):
     x = synth.pcm_to_f32(synth.segment_pcm(1234))
     feat, det, dbg = run(emu, x[None], nranks, nwarps)
@@ -112,3 +112,13 @@ def test_batch_rows_are_independent(emu):
     for i in range(3):
         f1, d1, _ = run(emu, pcm[i:i + 1], 4, 2)
         assert np.array_equal(fb[i], f1[0])
+
+
+@pytest.mark.parametrize("T,nranks", [(30001, 2), (30001, 1), (257, 1), (513, 1), (1025, 2), (80127, 4), (80129, 1)])
+def test_every_sample_is_reconstructed_once(emu, T, nranks):
+    """det[72] counts the samples of the STFT -> ISTFT residual: all T of them, whatever T mod 128 is."""
+    x = synth.pcm_to_f32(synth.segment_pcm(77, T))
+    feat, det, _ = run(emu, x[None], nranks, 4)
+    assert det[0, 72] == T
+    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6
+    check_against_oracle(det[0], feat[0], x)

@@ -33,10 +33,10 @@ def test_capacity_queries_without_device(built):
     from msa_b200 import _lib
     l = _lib.lib()
     assert l.msa_version() >= 100
-    assert l.msa_features_cluster_size(80000) == 4
+    assert l.msa_features_cluster_size(80000) == 1                        # a 5 s segment fits one CTA
     assert l.msa_features_cluster_size(8000) == 1
-    assert l.msa_features_cluster_size(160000) == 8
-    assert l.msa_features_cluster_size(320000) == 16
+    assert l.msa_features_cluster_size(160000) == 2
+    assert l.msa_features_cluster_size(960000) == 8
     assert l.msa_features_cluster_size(2_000_000) == 0                    # unsupported: too long for one cluster
     assert 0 < l.msa_features_smem_bytes(80000, 4) <= 232448
     assert l.msa_fusion_num_tensors() == 42
