@@ -3,7 +3,7 @@
 #include "../../include/msa_b200.h"
 
 namespace msa {
-constexpr int kFeatThreads = 512;      // default threads per feature CTA (16 warps x <= 128 registers)
+constexpr int kFeatThreads = 256;      // default threads per feature CTA: 8 warps x 128 registers, two CTAs per SM
 constexpr int kNumSms = 148;
 constexpr int kMaxSmem = 232448;   // 227 KB opt-in shared memory per CTA on sm_100
 void reset_launches();

@@ -24,7 +24,11 @@ struct GpuEnv {
 
   // one sample as fp32 (int16 PCM is scaled by 1/32768 like torchaudio.load)
   __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
-  __device__ __forceinline__ float ld(const int16_t* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
+  // int16 -> fp32 on the integer/FMA pipes instead of the quarter-rate I2F: 1.5 * 2^23 + v is exact in fp32
+  static __device__ __forceinline__ float s16_to_f32(int v) {
+    return (__int_as_float(0x4B400000 + v) - 12582912.0f) * (1.0f / 32768.0f);
+  }
+  __device__ __forceinline__ float ld(const int16_t* p) { return s16_to_f32((int)__ldg(p)); }
 
   // samples idx .. idx+3 of a segment of T samples (0 beyond the end), one vector load when aligned
   __device__ __forceinline__ void ld4(const float* x, int idx, int T, float* v) {
@@ -39,14 +43,13 @@ struct GpuEnv {
   }
   __device__ __forceinline__ void ld4(const int16_t* x, int idx, int T, float* v) {
     const int16_t* p = x + idx;
-    const float k = 1.0f / 32768.0f;
     if (idx + 3 < T && (reinterpret_cast<uintptr_t>(p) & 7) == 0) {
       const int2 q = __ldg(reinterpret_cast<const int2*>(p));
-      v[0] = (float)(short)(q.x & 0xffff) * k; v[1] = (float)(short)(q.x >> 16) * k;
-      v[2] = (float)(short)(q.y & 0xffff) * k; v[3] = (float)(short)(q.y >> 16) * k;
+      v[0] = s16_to_f32((int)(short)(q.x & 0xffff)); v[1] = s16_to_f32(q.x >> 16);
+      v[2] = s16_to_f32((int)(short)(q.y & 0xffff)); v[3] = s16_to_f32(q.y >> 16);
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? (float)__ldg(p + i) * k : 0.0f;
+      for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? s16_to_f32((int)__ldg(p + i)) : 0.0f;
     }
   }
 
@@ -55,6 +58,25 @@ struct GpuEnv {
     const int4* s = reinterpret_cast<const int4*>(src);
     int4* d = reinterpret_cast<int4*>(dst);
     for (int i = tid; i < bytes / 16; i += nthreads) d[i] = __ldg(s + i);
+  }
+
+  // op over the 32 lanes' values (butterfly of shuffles: every lane gets the same, deterministic result)
+  template <class G> __device__ __forceinline__ double warp_reduce(int op, G&& get) {
+    double v = get(0);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v = red_comb(op, v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+  }
+
+  // append (key, value) of the lanes with `pred` to a per-warp list in lane order; `cnt` is warp-uniform
+  // and keeps counting past `cap` (overflow is the caller's signal)
+  __device__ __forceinline__ void push(bool pred, int2* list, int& cnt, int cap, int key, float val) {
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m) {
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (pred && pos < cap) list[pos] = make_int2(key, __float_as_int(val));
+      cnt += __popc(m);
+    }
   }
 
   // dynamic work distribution: one shared-memory counter per CTA, one atomic per warp and task

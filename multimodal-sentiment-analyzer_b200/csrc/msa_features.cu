@@ -10,7 +10,7 @@
 namespace msa {
 
 template <class InT, int THREADS>
-__global__ void __launch_bounds__(THREADS, 1) features_kernel(const FeatParams P) {
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) features_kernel(const FeatParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   GpuEnv env;

@@ -40,6 +40,7 @@
 // logic can be exercised without a GPU.  It must only use the Env primitives.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include "msa_fft.cuh"
 #include "msa_hd.h"
 #include "msa_tables.hpp"
@@ -53,6 +54,10 @@ constexpr int kWarpBufBytes = 2 * kFftHalf * 8;  // two tiles per warp
 constexpr int kTailFloats = 3 * kHopP;           // the 3 hop-blocks a quad leaves to its successor
 constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
 constexpr int kRedSlots = 16;
+constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
+constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (the largest MFCC use of a warp's buffer)
+// top_db candidates of one warp live behind the transpose tile: 198 entries of (frame << 7 | filter, dB)
+constexpr int kClampCap = (kWarpBufBytes - kShareBytes) / 8;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
 enum : int { kFlagStrictNan = 1 };
@@ -75,17 +80,26 @@ struct Partials {
   double mf_sum[kMfcc];
   double mf_sumsq, mf_abs_lo, mf_abs_hi;
   double p_n, p_sum, p_sumsq;
-  double e_total, e_noise;
-  float db_max, db_min, p_max;
+  double e_total, e_noise, e_left;
+  float db_max, db_min, p_max, a_max;
   int mf_frames, n_atoms, slow_pass;
 };
 
 struct FeatLayout {
-  int buf_off, tail_off, mfl_off, atoms_off, tab_off, out_off, part_off, ctr_off;
+  int buf_off, tail_off, mfl_off, atoms_off, tab_off, wred_off, out_off, part_off, ctr_off;
   int mfl_frames, atoms_cap, total;
 };
 
 MSA_FN int ceil_div(int a, int b) { return (a + b - 1) / b; }
+MSA_FN float int_as_float(int v) {
+#ifdef __CUDACC__
+  return __int_as_float(v);
+#else
+  float f;
+  std::memcpy(&f, &v, 4);
+  return f;
+#endif
+}
 
 // identical on host (launch configuration) and device (carve-up)
 inline
@@ -100,15 +114,16 @@ FeatLayout feat_layout(int T, int nranks, int nwarps) {
   l.mfl_frames = 4 * ((((nFm + 3) / 4) + nranks - 1) / nranks);
   l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
   int buf = nwarps * kWarpBufBytes;
-  const int red = (kRedSlots * (nwarps * 32 + 32)) * 8;        // block-reduction scratch aliases the FFT tiles
   const int gather = (T / kAtom + 8) * 4;                      // rank 0 gathers all energy atoms there at the end
-  if (buf < red) buf = red;
   if (buf < gather) buf = gather;
   l.buf_off = take(buf);
-  l.tail_off = take((nwarps + 1) * kTailFloats * 4);
-  l.mfl_off = take(l.mfl_frames * kMfcc * 4);
+  // the overlap-add tails ("pitch" phase) and the MFCC rows (written after it) share one region
+  int tm = (nwarps + 1) * kTailFloats * 4;
+  if (tm < l.mfl_frames * kMfcc * 4) tm = l.mfl_frames * kMfcc * 4;
+  l.tail_off = l.mfl_off = take(tm);
   l.atoms_off = take(l.atoms_cap * 4);
   l.tab_off = take((int)sizeof(SmemTables));
+  l.wred_off = take(kRedSlots * nwarps * 8);
   l.out_off = take(kRedSlots * 8);
   l.part_off = take((int)sizeof(Partials));
   l.ctr_off = take(16);
@@ -144,30 +159,23 @@ MSA_FN double red_comb(int op, double a, double b) {
 }
 
 // Deterministic block reduction of K per-lane doubles: out[k] (shared memory) = op_k over all threads.
+// Level 1 is the Env's warp reduction (shuffles on the GPU), level 2 combines the per-warp values.
 template <int K, class Env, class Get>
-MSA_KFN void block_reduce(Env& env, double* red, double* out, const int* ops, Get get) {
+MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, Get get) {
   static_assert(K <= kRedSlots, "reduction scratch");
-  const int NT = env.nthreads;
-  env.lanes([&](int lane, int li) {
+  const int NW = env.nwarps;
 #pragma unroll
-    for (int k = 0; k < K; ++k) red[k * NT + env.warp * 32 + lane] = get(li, k);
-  });
+  for (int k = 0; k < K; ++k) {
+    const double r = env.warp_reduce(ops[k], [&](int li) { return get(li, k); });
+    env.lanes([&](int lane, int li) { (void)li; if (lane == 0) wred[k * NW + env.warp] = r; });
+  }
   env.sync();
   if (env.warp == 0) {
     env.lanes([&](int lane, int li) {
       (void)li;
-      for (int k = 0; k < K; ++k) {
-        double a = red[k * NT + lane];
-        for (int w = 1; w < env.nwarps; ++w) a = red_comb(ops[k], a, red[k * NT + w * 32 + lane]);
-        red[K * NT + k * 32 + lane] = a;
-      }
-    });
-    env.wsync();
-    env.lanes([&](int lane, int li) {
-      (void)li;
       if (lane < K) {
-        double a = red[K * NT + lane * 32];
-        for (int j = 1; j < 32; ++j) a = red_comb(ops[lane], a, red[K * NT + lane * 32 + j]);
+        double a = wred[lane * NW];
+        for (int w = 1; w < NW; ++w) a = red_comb(ops[lane], a, wred[lane * NW + w]);
         out[lane] = a;
       }
     });
@@ -184,7 +192,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   const InT* x = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T;
 
   c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
-  double* red = reinterpret_cast<double*>(smem + lay.buf_off);
+  double* wred = reinterpret_cast<double*>(smem + lay.wred_off);
   float* tails = reinterpret_cast<float*>(smem + lay.tail_off);
   float* mfl = reinterpret_cast<float*>(smem + lay.mfl_off);
   float* atoms = reinterpret_cast<float*>(smem + lay.atoms_off);
@@ -204,7 +212,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   // ---------------------------------------------------------------- stage the constant tables
   env.copy16(smem + lay.tab_off, &P.tab->s, (int)sizeof(SmemTables));
-  if (env.warp == 0) env.lanes([&](int lane, int li) { (void)li; if (lane < 4) ctr[lane] = 0; });
+  if (env.warp == 0) env.lanes([&](int lane, int li) { (void)li; if (lane < 4) ctr[lane] = 0; });   // task counters of the two MFCC passes, overflow flag
   env.sync();
 
   // ---------------------------------------------------------------- K1: energy atoms, totals
@@ -212,8 +220,9 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   // shared-memory tile turns the per-lane partial sums into per-atom sums (20 entries each)
   int n_atoms_local = 0;
   {
-    double e_tot[S], e_noi[S];
-    for (int i = 0; i < S; ++i) e_tot[i] = e_noi[i] = 0.0;
+    double e_tot[S], e_noi[S], e_left[S];
+    float a_max[S];
+    for (int i = 0; i < S; ++i) { e_tot[i] = e_noi[i] = e_left[i] = 0.0; a_max[i] = 0.0f; }
     if (P.parts & kPartWave) {
       const int nG = ceil_div(T, kGroup);
       const int gper = ceil_div(nG, NR);
@@ -240,14 +249,16 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         });
         env.wsync();
         env.lanes([&](int lane, int li) {
-          (void)li;
           if (lane < 8) {
             const int a = g * 8 + lane;
-            if (a < full_atoms) {
-              float s = 0.0f;
+            float s = 0.0f;
 #pragma unroll
-              for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
+            for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
+            if (a < full_atoms) {
               atoms[a - a_lo] = s;
+              a_max[li] = fmaxf(a_max[li], s);
+            } else {
+              e_left[li] += (double)s;                     // the T mod 80 samples behind the last full atom
             }
           }
         });
@@ -267,10 +278,14 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         e_noi[li] = (double)acc;
       });
     }
-    env.sync();                                           // the reduction scratch aliases every warp's tiles
-    const int ops[2] = {kOpSum, kOpSum};
-    block_reduce<2>(env, red, rout, ops, [&](int li, int k) { return k == 0 ? e_tot[li] : e_noi[li]; });
-    if (env.tid == 0) { part->e_total = rout[0]; part->e_noise = rout[1]; part->n_atoms = n_atoms_local; }
+    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
+    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
+      return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
+    });
+    if (env.tid == 0) {
+      part->e_total = rout[0]; part->e_noise = rout[1]; part->e_left = rout[2]; part->a_max = (float)rout[3];
+      part->n_atoms = n_atoms_local;
+    }
   }
 
   // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual
@@ -351,7 +366,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               pass_a_inv<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
               static_for<0, 16>([&](auto nc) {
                 constexpr int n1 = decltype(nc)::value;
-                const float w = tb->win512s[32 * n1 + lane];
+                const float w = tb->win512[32 * n1 + lane];    // the 1/512 of the unnormalised inverse lives in ienv
                 if (h == 0) {
                   own[li][n1 / 4][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4][n1 % 4]);
                   own[li][n1 / 4 + 1][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 1][n1 % 4]);
@@ -400,7 +415,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                     const int f = b0 + b - j;
                     if (f >= 0 && f < nFp) { const float w = tb->win512[j * kHopP + o]; e = fmaf(w, w, e); }
                   }
-                  const float pv = fabsf(env.ld(x + t) - y / e);
+                  const float pv = fabsf(env.ld(x + t) - y / (e * (float)kNfftP));
                   s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
                 }
               }
@@ -421,7 +436,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       env.sync();
     }
     const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    block_reduce<4>(env, red, rout, ops, [&](int li, int k) {
+    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
       return k == 0 ? ps[li] : (k == 1 ? pq[li] : (k == 2 ? pn[li] : (double)pmax[li]));
     });
     if (env.tid == 0) { part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3]; }
@@ -437,8 +452,11 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   const int mf_end = (4 * mq_end < nFm) ? 4 * mq_end : nFm;
   const int nfr = ((P.parts & kPartMfcc) && mf_end > mf_begin) ? mf_end - mf_begin : 0;
 
-  // One MFCC pass over this rank's quads.  thr = -inf in the first pass (no clamp on live filters).
-  auto mfcc_pass = [&](float thr, int* counter, float* dbmax_out, float* dbmin_out) {
+  // One MFCC pass over this rank's quads.  First pass: thr = -inf (no clamp on live filters) and every
+  // live (frame, filter) below `cand` dB goes on the warp's candidate list; clamped pass: cand = -inf.
+  int2* clist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(wbuf) + kShareBytes);
+  auto mfcc_pass = [&](float thr, float cand, int* counter, int* ncand_out, float* dbmax_out, float* dbmin_out) {
+    int ncand = 0;                                               // warp-uniform
     float dmax[S], dmin[S];
     for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
     float pw[S][28];
@@ -471,14 +489,14 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               const float w = tb->win400[25 * n1 + lane];
               z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
             }
-            pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kFftHalf);
+            pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kTileM);
           }
         });
       }
       env.wsync();
       env.lanes([&](int lane, int li) {
         (void)li;
-        c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow400;
+        c32* row = wbuf + (lane >> 4) * kTileM + (lane & 15) * kRow400;
         c32 v[25];
 #pragma unroll
         for (int i = 0; i < 25; ++i) v[i] = row[i];
@@ -492,7 +510,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       env.lanes([&](int lane, int li) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const c32* zt = wbuf + h * kFftHalf;
+          const c32* zt = wbuf + h * kTileM;
 #pragma unroll
           for (int i = 0; i < 7; ++i) {
             const int k = lane + 32 * i;
@@ -549,7 +567,9 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float d = 3.0102999566398120f * env.log2(fmaxf(e[j], 1e-10f));   // 10 log10(max(x, amin))
-            if (!dead && (m0 + j) < nFm) {
+            const bool live = !dead && (m0 + j) < nFm;
+            env.push(live && d < cand, clist, ncand, kClampCap, ((m0 + j - mf_begin) << 7) | (32 * s + lane), d);
+            if (live) {
               dmax[li] = fmaxf(dmax[li], d);
               dmin[li] = fminf(dmin[li], d);
               d = fmaxf(d, thr);
@@ -594,18 +614,37 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       });
       env.wsync();
     }
-    env.sync();
     const int ops[2] = {kOpMax, kOpMin};
-    block_reduce<2>(env, red, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
+    block_reduce<2>(env, wred, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
     *dbmax_out = (float)rout[0];
     *dbmin_out = (float)rout[1];
+    *ncand_out = ncand;
     env.sync();
   };
 
+  // An upper bound of the segment's largest mel energy, known before the pass: a frame holds at most 400
+  // samples of the reflect-padded signal, i.e. at most 8 energy atoms' worth (twice 4: a padded frame repeats
+  // up to 201 samples) plus the ragged end; Parseval with window <= 1 and mel weights <= 1 gives
+  // mel <= 400 * E_frame.  Anything 80 dB below the bound or higher can never be clamped by top_db.
+  env.csync();                                            // #0: every rank's atom maximum is visible
+  float cand = -3.0e38f;
+  {
+    double amax = 0.0, eleft = 0.0;
+    for (int rr = 0; rr < NR; ++rr) {
+      const Partials* rp = env.remote(part, rr);
+      amax = (amax > (double)rp->a_max) ? amax : (double)rp->a_max;
+      eleft += rp->e_left;
+    }
+    const float bound = (float)(400.0 * (8.0 * amax + 2.0 * eleft)) * 1.001f;
+    if (P.parts & kPartWave) cand = 3.0102999566398120f * env.log2(fmaxf(bound, 1e-30f)) - 80.0f + 0.01f;
+    else cand = 3.0e38f;                                  // no atoms: every live value is a candidate (overflow -> clamped pass)
+  }
   float dbmax = -3.0e38f, dbmin = 3.0e38f;
-  mfcc_pass(-3.0e38f, ctr, &dbmax, &dbmin);
+  int ncand = 0;
+  mfcc_pass(-3.0e38f, cand, ctr, &ncand, &dbmax, &dbmin);
+  if (ncand > kClampCap) env.lanes([&](int lane, int li) { (void)li; if (lane == 0) ctr[2] = 1; });
   if (env.tid == 0) { part->db_max = dbmax; part->db_min = dbmin; part->mf_frames = nfr; }
-  env.csync();                                            // #1: every rank's dB extrema are visible
+  env.csync();                                            // #1: every rank's dB extrema (and this CTA's overflow flag) are visible
 
   float gmax = -3.0e38f, gmin = 3.0e38f;
   for (int rr = 0; rr < NR; ++rr) {
@@ -613,12 +652,34 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     gmax = fmaxf(gmax, rp->db_max);
     gmin = fminf(gmin, rp->db_min);
   }
-  // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  Live filters below it are rare: redo the pass clamped.
+  // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  The DCT is linear, so a clamped value only
+  // adds dct[m][k] * (thr - dB) to its frame: every warp patches the frames it produced from its own
+  // candidate list (a frame belongs to exactly one warp; list order is program order: deterministic).
+  // A list that overflowed (long digital silence inside a loud segment) redoes this CTA's pass clamped.
   const float thr = gmax - 80.0f;
-  const bool slow = (P.parts & kPartMfcc) && (gmin < thr);
+  const bool fix = (P.parts & kPartMfcc) && (dbmin < thr);
+  const bool slow = fix && ctr[2] != 0;
   if (slow) {
     float a, b;
-    mfcc_pass(thr, ctr + 1, &a, &b);
+    int c;
+    mfcc_pass(thr, -3.0e38f, ctr + 1, &c, &a, &b);
+  } else if (fix) {
+    env.lanes([&](int lane, int li) {
+      (void)li;
+      if (lane < kMfcc) {
+        for (int e = 0; e < ncand; ++e) {
+          const int2 ce = clist[e];
+          const float d = int_as_float(ce.y);
+          if (d < thr) {
+            const int m = ce.x & 127, q = (m >> 5) * kMfcc + lane;
+            const float w = tb->dctq[((q >> 2) * 32 + (m & 31)) * 4 + (q & 3)];
+            float* o = mfl + (ce.x >> 7) * kMfcc + lane;
+            *o = fmaf(w, thr - d, *o);
+          }
+        }
+      }
+    });
+    env.sync();
   }
 
   // ---------------------------------------------------------------- MFCC moments (timbre z-score, clarity)
@@ -642,7 +703,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       }
     });
     const int ops[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    block_reduce<16>(env, red, rout, ops, [&](int li, int k) { return acc[li][k]; });
+    block_reduce<16>(env, wred, rout, ops, [&](int li, int k) { return acc[li][k]; });
     if (env.tid == 0) {
       for (int k = 0; k < kMfcc; ++k) part->mf_sum[k] = rout[k];
       part->mf_sumsq = rout[13]; part->mf_abs_lo = rout[14]; part->mf_abs_hi = rout[15];
@@ -686,9 +747,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       gs[li] = a; bs[li] = b;
     });
     const int ops2[2] = {kOpSum, kOpSum};
-    // the atoms live where the reduction scratch is: reduce through the tail tiles instead
-    double* red2 = reinterpret_cast<double*>(smem + lay.tail_off);
-    block_reduce<2>(env, red2, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
+    block_reduce<2>(env, wred, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
     const double gmean = (nG > 0) ? rout[0] / nG : 0.0;
     const double bmean = (nBk > 0) ? rout[1] / nBk : 0.0;
     env.sync();
@@ -698,7 +757,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       for (int k = env.warp * 32 + lane; k < nBk; k += env.nthreads) { const double d = block_ms(k) - bmean; b += d * d; }
       gs[li] = a; bs[li] = b;
     });
-    block_reduce<2>(env, red2, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
+    block_reduce<2>(env, wred, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
     const double gq = rout[0], bq = rout[1];
 
     if (env.tid == 0) {
@@ -810,8 +869,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         d[64] = gmax; d[65] = (float)p_mean; d[66] = (float)p_std; d[67] = tot.p_max;
         d[68] = (float)tot.e_total; d[69] = (float)tot.e_noise; d[70] = (float)tot.mf_frames; d[71] = (float)nG;
         d[72] = (float)tot.p_n; d[73] = (float)nBk; d[74] = (float)nA;
-        d[75] = slow ? 1.0f : 0.0f; d[76] = gmin;
-        for (int k = 77; k < kDetailStride; ++k) d[k] = 0.0f;
+        d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
+        for (int k = 79; k < kDetailStride; ++k) d[k] = 0.0f;
       }
     }
   }

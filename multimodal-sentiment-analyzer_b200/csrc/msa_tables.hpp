@@ -37,8 +37,8 @@ struct alignas(16) SmemTables {
   float tw400[2 * 15 * 32];       // [(k1-1)*32 + n2] = W_400^(n2 k1), n2 < 25
   float win400[kNfftM];
   float win512[kNfftP];
-  float win512s[kNfftP];          // synthesis window / 512 (the unnormalised inverse FFT scale)
-  float ienv[kHopP];              // 1 / sum_j win512[j*128 + o]^2 : interior window envelope of torch.istft
+  float ienv[kHopP];              // 1 / (512 sum_j win512[j*128 + o]^2): interior window envelope of torch.istft
+                                  // times the 1/512 of the unnormalised inverse FFT (exact: power of two)
   float mel_w[kMelTrips * 32];    // [(trip offset of slot s + p)*32 + lane], zero padded
   float dctq[kDctQuads * 32 * 4]; // float4 [i*32 + lane]: flattened (slot, k) = divmod(4 i + c, 13); 0 for empty filters
   float dct_dead[16];             // sum over the empty filters of dct[m][k]
@@ -60,14 +60,11 @@ inline int build_feature_tables(FeatureTables& ft) {
   SmemTables& t = ft.s;
   const double PI = 3.14159265358979323846;
   for (int n = 0; n < kNfftM; ++n) t.win400[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftM));
-  for (int n = 0; n < kNfftP; ++n) {
-    t.win512[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP));
-    t.win512s[n] = t.win512[n] * (1.0f / (float)kNfftP);          // exact: power of two
-  }
+  for (int n = 0; n < kNfftP; ++n) t.win512[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP));
   for (int o = 0; o < kHopP; ++o) {
     float e = 0.0f;
     for (int j = 0; j < 4; ++j) e += t.win512[j * kHopP + o] * t.win512[j * kHopP + o];
-    t.ienv[o] = 1.0f / e;
+    t.ienv[o] = (1.0f / e) * (1.0f / (float)kNfftP);
   }
   for (int k1 = 1; k1 < 16; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {

@@ -19,6 +19,7 @@
 #include <vector>
 
 struct float4 { float x, y, z, w; };
+struct int2 { int x, y; };
 
 #include "msa_features_body.cuh"
 
@@ -53,6 +54,16 @@ struct CpuEnv {
   }
   void copy16(void* dst, const void* src, int bytes) {
     if (warp == 0) std::memcpy(dst, src, bytes);
+  }
+  template <class G> double warp_reduce(int op, G&& get) {
+    double a = get(0);
+    for (int l = 1; l < 32; ++l) a = red_comb(op, a, get(l));
+    return a;
+  }
+  void push(bool pred, int2* list, int& cnt, int cap, int key, float val) {   // lanes run in order: same list order as the GPU
+    if (!pred) return;
+    if (cnt < cap) { int bits; std::memcpy(&bits, &val, 4); list[cnt] = int2{key, bits}; }
+    ++cnt;
   }
   int next_task(int* ctr) { return __atomic_fetch_add(ctr, 1, __ATOMIC_RELAXED); }
 };

@@ -122,3 +122,17 @@ def test_every_sample_is_reconstructed_once(emu, T, nranks):
     assert det[0, 72] == T
     assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6
     check_against_oracle(det[0], feat[0], x)
+
+
+@pytest.mark.parametrize("name,fix,slow", [("seg1234", 1, 0), ("white_0p1", 0, 0), ("tone_220", 1, 1), ("half_silence", 1, 1)])
+def test_top_db_clamp_paths(emu, name, fix, slow):
+    """amplitude_to_DB(top_db=80): values 80 dB below the segment maximum are clamped.  The kernel patches
+    the few affected frames from per-warp candidate lists (det[78]) and only redoes the pass when a list
+    overflows (det[75]); both paths and the no-clamp path must give the reference MFCC."""
+    x = synth.pcm_to_f32(synth.segment_pcm(1234)) if name == "seg1234" else synth.adversarial_cases()[name]
+    for nranks, nwarps in ((1, 8), (2, 4)):
+        _, det, dbg = run(emu, x[None], nranks, nwarps)
+        assert (det[0, 78], det[0, 75]) == (fix, slow)
+        assert det[0, 64] - 80.0 <= det[0, 77]                               # candidate level never below the real threshold
+        ref = fx.mfcc(x.astype(np.float64)).T
+        assert np.abs(dbg[0] - ref).max() < 1e-3

@@ -79,7 +79,7 @@ def test_cluster_sizes_agree_with_oracle(ana, cluster, T):
     assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6               # STFT -> ISTFT residual: std, max
     assert det[0, 72] == T                                       # every sample reconstructed exactly once
     from msa_b200 import _lib
-    assert ana._lib.msa_features_f32(_lib.ptr(torch.zeros(1, 320000, device=ana.device)), 1, 320000, None,
+    assert ana._lib.msa_features_f32(_lib.ptr(torch.zeros(1, 800000, device=ana.device)), 1, 800000, None,
                                      _lib.ptr(torch.zeros(1, 31, device=ana.device)), None, None, 1, 7, 1, None) == -2   # too long for 1 CTA
 
 
