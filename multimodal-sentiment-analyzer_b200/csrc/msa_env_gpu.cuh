@@ -26,7 +26,8 @@ struct GpuEnv {
   __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
   // int16 -> fp32 on the integer/FMA pipes instead of the quarter-rate I2F: 1.5 * 2^23 + v is exact in fp32
   static __device__ __forceinline__ float s16_to_f32(int v) {
-    return (__int_as_float(0x4B400000 + v) - 12582912.0f) * (1.0f / 32768.0f);
+    // (12582912 + v) * 2^-15 - 384 in one FMA: every intermediate is exactly representable
+    return __fmaf_rn(__int_as_float(0x4B400000 + v), 1.0f / 32768.0f, -384.0f);
   }
   __device__ __forceinline__ float ld(const int16_t* p) { return s16_to_f32((int)__ldg(p)); }
 

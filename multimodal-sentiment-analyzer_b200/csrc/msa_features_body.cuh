@@ -217,7 +217,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   // ---------------------------------------------------------------- K1: energy atoms, totals
   // groups of 640 samples (8 atoms of 80): lane l loads float4 j at sample 128 j + 4 l, a 160-entry
-  // shared-memory tile turns the per-lane partial sums into per-atom sums (20 entries each)
+  // shared-memory tile per group turns the per-lane partial sums into per-atom sums (20 entries each)
   int n_atoms_local = 0;
   {
     double e_tot[S], e_noi[S], e_left[S];
@@ -233,24 +233,35 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
       n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
       float* scr = reinterpret_cast<float*>(wbuf);
-      for (int g = g0 + env.warp; g < g1; g += NW) {
-        const int base = g * kGroup;
+      // two groups (10 float4 per lane) are in flight per step: this phase is pure load latency
+      for (int gp = g0 + 2 * env.warp; gp < g1; gp += 2 * NW) {
+        const int ng = (gp + 1 < g1) ? 2 : 1;
         env.lanes([&](int lane, int li) {
-          float acc = 0.0f;
+          float v[2][5][4];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            float v[4];
-            env.ld4(x, base + 128 * j + 4 * lane, T, v);
-            const float s = fmaf(v[3], v[3], fmaf(v[2], v[2], fmaf(v[1], v[1], v[0] * v[0])));
-            scr[32 * j + lane] = s;
-            acc += s;
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              if (u < ng) env.ld4(x, (gp + u) * kGroup + 128 * j + 4 * lane, T, v[u][j]);
+              else v[u][j][0] = v[u][j][1] = v[u][j][2] = v[u][j][3] = 0.0f;
+            }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+              const float* q = v[u][j];
+              const float s = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
+              scr[160 * u + 32 * j + lane] = s;
+              acc += s;
+            }
+            e_tot[li] += (double)acc;
           }
-          e_tot[li] += (double)acc;
         });
         env.wsync();
         env.lanes([&](int lane, int li) {
-          if (lane < 8) {
-            const int a = g * 8 + lane;
+          if (lane < 8 * ng) {
+            const int a = gp * 8 + lane;
             float s = 0.0f;
 #pragma unroll
             for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
@@ -306,6 +317,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int ntasks = (q_end > q_begin) ? q_end - q_first : 0;
       const int niter = ceil_div(ntasks, NW);
       float own[S][7][4];
+      float xv[S][4][4];                                           // the input samples the quad's 4 own blocks are compared with
       for (int it = 0; it < niter; ++it) {
         const int task = it * NW + env.warp;
         const bool active = task < ntasks;
@@ -385,6 +397,18 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) t[b * kHopP + 32 * i + lane] = own[li][4 + b][i];
           });
+          // issue the loads of the comparison samples now: their latency hides behind the barrier
+          if (quad >= q_begin) {
+            env.lanes([&](int lane, int li) {
+#pragma unroll
+              for (int b = 0; b < 4; ++b)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int t = kHopP * (f0 + b) + 32 * i + lane - kNfftP / 2;
+                  xv[li][b][i] = (t >= 0 && t < T) ? env.ld(x + t) : 0.0f;
+                }
+            });
+          }
         }
         env.sync();
         if (active && quad >= q_begin) {
@@ -406,7 +430,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                 float y = own[li][b][i];
                 if (b < 3 && has_prev) y += pt[b * kHopP + o];
                 if (fast) {
-                  const float pv = fabsf(env.ld(x + t) - y * tb->ienv[o]);
+                  const float pv = fabsf(xv[li][b][i] - y * tb->ienv[o]);
                   s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
                 } else if (t >= 0 && t < T) {
                   float e = 0.0f;
@@ -415,7 +439,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                     const int f = b0 + b - j;
                     if (f >= 0 && f < nFp) { const float w = tb->win512[j * kHopP + o]; e = fmaf(w, w, e); }
                   }
-                  const float pv = fabsf(env.ld(x + t) - y / (e * (float)kNfftP));
+                  const float pv = fabsf(xv[li][b][i] - y / (e * (float)kNfftP));
                   s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
                 }
               }
@@ -452,176 +476,10 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   const int mf_end = (4 * mq_end < nFm) ? 4 * mq_end : nFm;
   const int nfr = ((P.parts & kPartMfcc) && mf_end > mf_begin) ? mf_end - mf_begin : 0;
 
-  // One MFCC pass over this rank's quads.  First pass: thr = -inf (no clamp on live filters) and every
-  // live (frame, filter) below `cand` dB goes on the warp's candidate list; clamped pass: cand = -inf.
+  // MFCC passes over this rank's quads.  Pass 0: no clamp on live filters (thr = -inf) and every live
+  // (frame, filter) below `cand` dB goes on the warp's candidate list.  Pass 1 (only when a candidate
+  // list overflowed) redoes the quads clamped at the now known threshold.
   int2* clist = reinterpret_cast<int2*>(reinterpret_cast<unsigned char*>(wbuf) + kShareBytes);
-  auto mfcc_pass = [&](float thr, float cand, int* counter, int* ncand_out, float* dbmax_out, float* dbmin_out) {
-    int ncand = 0;                                               // warp-uniform
-    float dmax[S], dmin[S];
-    for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
-    float pw[S][28];
-    float share[S][52];
-    float* fbuf = reinterpret_cast<float*>(wbuf);
-    const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
-    for (;;) {
-      const int task = env.next_task(counter);
-      if (task >= ntasks) break;
-      const int m0 = 4 * (mq_begin + task);
-      const int s0 = kHopM * m0 - kNfftM / 2;
-      const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);
-      for (int h = 0; h < 2; ++h) {
-        env.lanes([&](int lane, int li) {
-          (void)li;
-          if (lane < 25) {
-            const int sb = s0 + 2 * h * kHopM;
-            const bool oka = (m0 + 2 * h) < nFm, okb = (m0 + 2 * h + 1) < nFm;
-            float raw[24];
-            if (interior) {
-#pragma unroll
-              for (int i = 0; i < 24; ++i) raw[i] = env.ld(x + sb + 25 * i + lane);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 24; ++i) raw[i] = xr(sb + 25 * i + lane);
-            }
-            c32 z[16];
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-              const float w = tb->win400[25 * n1 + lane];
-              z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
-            }
-            pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kTileM);
-          }
-        });
-      }
-      env.wsync();
-      env.lanes([&](int lane, int li) {
-        (void)li;
-        c32* row = wbuf + (lane >> 4) * kTileM + (lane & 15) * kRow400;
-        c32 v[25];
-#pragma unroll
-        for (int i = 0; i < 25; ++i) v[i] = row[i];
-        dft25<false>(v);
-#pragma unroll
-        for (int i = 0; i < 25; ++i) row[i] = v[i];                // row[k2] = Z[k1 + 16 k2]
-      });
-      env.wsync();
-      // power of both packed frames: with Z = FFT(a + i b),
-      //   |A_k|^2 = |Z_k + conj Z_{N-k}|^2 / 4,  |B_k|^2 = |Z_k - conj Z_{N-k}|^2 / 4
-      env.lanes([&](int lane, int li) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const c32* zt = wbuf + h * kTileM;
-#pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int k = lane + 32 * i;
-            float pa = 0.0f, pb = 0.0f;
-            if (k < kBinsM) {
-              const int kk = (k == 0) ? 0 : kNfftM - k;
-              const c32 zk = zt[(k & 15) * kRow400 + (k >> 4)];
-              const c32 zn = zt[(kk & 15) * kRow400 + (kk >> 4)];
-              const float sx = zk.x + zn.x, sy = zk.y - zn.y;
-              const float dx = zk.x - zn.x, dy = zk.y + zn.y;
-              pa = 0.25f * fmaf(sx, sx, sy * sy);
-              pb = 0.25f * fmaf(dx, dx, dy * dy);
-            }
-            pw[li][14 * h + 2 * i] = pa;
-            pw[li][14 * h + 2 * i + 1] = pb;
-          }
-        }
-      });
-      env.wsync();
-      env.lanes([&](int lane, int li) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          float* pr = fbuf + h * (2 * kFftHalf);                    // same bytes as tile h, as floats
-#pragma unroll
-          for (int i = 0; i < 7; ++i) {
-            const int k = lane + 32 * i;
-            if (k < kPowStride) {                                  // bins 201..207 are written as zeros
-              pr[k] = pw[li][14 * h + 2 * i];
-              pr[kPowStride + k] = pw[li][14 * h + 2 * i + 1];
-            }
-          }
-        }
-      });
-      env.wsync();
-      // mel energies of the lane's 4 filters for the 4 frames, dB, DCT shares
-      env.lanes([&](int lane, int li) {
-        float db[4][4];                                            // [frame][slot]
-        static_for<0, 4>([&](auto sc) {
-          constexpr int s = decltype(sc)::value;
-          constexpr int trips = (s == 0) ? kMelTrip0 : (s == 1) ? kMelTrip1 : (s == 2) ? kMelTrip2 : kMelTrip3;
-          constexpr int toff = (s == 0) ? 0 : (s == 1) ? kMelTrip0 : (s == 2) ? kMelTrip0 + kMelTrip1 : kMelTrip0 + kMelTrip1 + kMelTrip2;
-          const int lo = tb->mel_lo[32 * s + lane];
-          const bool dead = tb->mel_dead[32 * s + lane] != 0;
-          float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
-#pragma unroll
-          for (int p = 0; p < trips; ++p) {
-            const float w = tb->mel_w[(toff + p) * 32 + lane];
-            e0 = fmaf(w, fbuf[lo + p], e0);
-            e1 = fmaf(w, fbuf[kPowStride + lo + p], e1);
-            e2 = fmaf(w, fbuf[2 * kFftHalf + lo + p], e2);
-            e3 = fmaf(w, fbuf[2 * kFftHalf + kPowStride + lo + p], e3);
-          }
-          const float e[4] = {e0, e1, e2, e3};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float d = 3.0102999566398120f * env.log2(fmaxf(e[j], 1e-10f));   // 10 log10(max(x, amin))
-            const bool live = !dead && (m0 + j) < nFm;
-            env.push(live && d < cand, clist, ncand, kClampCap, ((m0 + j - mf_begin) << 7) | (32 * s + lane), d);
-            if (live) {
-              dmax[li] = fmaxf(dmax[li], d);
-              dmin[li] = fminf(dmin[li], d);
-              d = fmaxf(d, thr);
-            }
-            db[j][s] = d;
-          }
-        });
-#pragma unroll
-        for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
-        const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
-        static_for<0, kDctQuads>([&](auto ic) {
-          constexpr int i = decltype(ic)::value;
-          const float4 q = dq[i * 32 + lane];
-          const float qc[4] = {q.x, q.y, q.z, q.w};
-          static_for<0, 4>([&](auto cc) {
-            constexpr int c = decltype(cc)::value;
-            constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(db[j][s], qc[c], share[li][j * kMfcc + k]);
-          });
-        });
-      });
-      env.wsync();
-      env.lanes([&](int lane, int li) {
-#pragma unroll
-        for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
-      });
-      env.wsync();
-      env.lanes([&](int lane, int li) {
-        (void)li;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int v = lane + 32 * half;
-          if (v < 52) {
-            float a = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) a += fbuf[v * 33 + j];
-            const int fr = m0 + v / kMfcc;
-            if (fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = a;
-          }
-        }
-      });
-      env.wsync();
-    }
-    const int ops[2] = {kOpMax, kOpMin};
-    block_reduce<2>(env, wred, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
-    *dbmax_out = (float)rout[0];
-    *dbmin_out = (float)rout[1];
-    *ncand_out = ncand;
-    env.sync();
-  };
-
   // An upper bound of the segment's largest mel energy, known before the pass: a frame holds at most 400
   // samples of the reflect-padded signal, i.e. at most 8 energy atoms' worth (twice 4: a padded frame repeats
   // up to 201 samples) plus the ragged end; Parseval with window <= 1 and mel weights <= 1 gives
@@ -639,31 +497,191 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     if (P.parts & kPartWave) cand = 3.0102999566398120f * env.log2(fmaxf(bound, 1e-30f)) - 80.0f + 0.01f;
     else cand = 3.0e38f;                                  // no atoms: every live value is a candidate (overflow -> clamped pass)
   }
-  float dbmax = -3.0e38f, dbmin = 3.0e38f;
-  int ncand = 0;
-  mfcc_pass(-3.0e38f, cand, ctr, &ncand, &dbmax, &dbmin);
-  if (ncand > kClampCap) env.lanes([&](int lane, int li) { (void)li; if (lane == 0) ctr[2] = 1; });
-  if (env.tid == 0) { part->db_max = dbmax; part->db_min = dbmin; part->mf_frames = nfr; }
-  env.csync();                                            // #1: every rank's dB extrema (and this CTA's overflow flag) are visible
-
-  float gmax = -3.0e38f, gmin = 3.0e38f;
-  for (int rr = 0; rr < NR; ++rr) {
-    const Partials* rp = env.remote(part, rr);
-    gmax = fmaxf(gmax, rp->db_max);
-    gmin = fminf(gmin, rp->db_min);
+  float thr = -3.0e38f, gmax = -3.0e38f, gmin = 3.0e38f;
+  int ncand = 0;                                           // warp-uniform length of this warp's candidate list
+  bool fix = false, slow = false;
+  for (int pass = 0; pass < 2; ++pass) {
+    const float cand_p = (pass == 0) ? cand : -3.0e38f;
+    int* counter = ctr + pass;
+      float dmax[S], dmin[S];
+      for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
+      float pw[S][28];
+      float share[S][52];
+      float* fbuf = reinterpret_cast<float*>(wbuf);
+      const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
+      for (;;) {
+        const int task = env.next_task(counter);
+        if (task >= ntasks) break;
+        const int m0 = 4 * (mq_begin + task);
+        const int s0 = kHopM * m0 - kNfftM / 2;
+        const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);
+        for (int h = 0; h < 2; ++h) {
+          env.lanes([&](int lane, int li) {
+            (void)li;
+            if (lane < 25) {
+              const int sb = s0 + 2 * h * kHopM;
+              const bool oka = (m0 + 2 * h) < nFm, okb = (m0 + 2 * h + 1) < nFm;
+              float raw[24];
+              if (interior) {
+  #pragma unroll
+                for (int i = 0; i < 24; ++i) raw[i] = env.ld(x + sb + 25 * i + lane);
+              } else {
+  #pragma unroll
+                for (int i = 0; i < 24; ++i) raw[i] = xr(sb + 25 * i + lane);
+              }
+              c32 z[16];
+  #pragma unroll
+              for (int n1 = 0; n1 < 16; ++n1) {
+                const float w = tb->win400[25 * n1 + lane];
+                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
+              }
+              pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kTileM);
+            }
+          });
+        }
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          c32* row = wbuf + (lane >> 4) * kTileM + (lane & 15) * kRow400;
+          c32 v[25];
+  #pragma unroll
+          for (int i = 0; i < 25; ++i) v[i] = row[i];
+          dft25<false>(v);
+  #pragma unroll
+          for (int i = 0; i < 25; ++i) row[i] = v[i];                // row[k2] = Z[k1 + 16 k2]
+        });
+        env.wsync();
+        // power of both packed frames: with Z = FFT(a + i b),
+        //   |A_k|^2 = |Z_k + conj Z_{N-k}|^2 / 4,  |B_k|^2 = |Z_k - conj Z_{N-k}|^2 / 4
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const c32* zt = wbuf + h * kTileM;
+  #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+              const int k = lane + 32 * i;
+              float pa = 0.0f, pb = 0.0f;
+              if (k < kBinsM) {
+                const int kk = (k == 0) ? 0 : kNfftM - k;
+                const c32 zk = zt[(k & 15) * kRow400 + (k >> 4)];
+                const c32 zn = zt[(kk & 15) * kRow400 + (kk >> 4)];
+                const float sx = zk.x + zn.x, sy = zk.y - zn.y;
+                const float dx = zk.x - zn.x, dy = zk.y + zn.y;
+                pa = 0.25f * fmaf(sx, sx, sy * sy);
+                pb = 0.25f * fmaf(dx, dx, dy * dy);
+              }
+              pw[li][14 * h + 2 * i] = pa;
+              pw[li][14 * h + 2 * i + 1] = pb;
+            }
+          }
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float* pr = fbuf + h * (2 * kFftHalf);                    // same bytes as tile h, as floats
+  #pragma unroll
+            for (int i = 0; i < 7; ++i) {
+              const int k = lane + 32 * i;
+              if (k < kPowStride) {                                  // bins 201..207 are written as zeros
+                pr[k] = pw[li][14 * h + 2 * i];
+                pr[kPowStride + k] = pw[li][14 * h + 2 * i + 1];
+              }
+            }
+          }
+        });
+        env.wsync();
+        // mel energies of the lane's 4 filters for the 4 frames, dB, DCT shares
+        env.lanes([&](int lane, int li) {
+          float db[4][4];                                            // [frame][slot]
+          static_for<0, 4>([&](auto sc) {
+            constexpr int s = decltype(sc)::value;
+            constexpr int trips = (s == 0) ? kMelTrip0 : (s == 1) ? kMelTrip1 : (s == 2) ? kMelTrip2 : kMelTrip3;
+            constexpr int toff = (s == 0) ? 0 : (s == 1) ? kMelTrip0 : (s == 2) ? kMelTrip0 + kMelTrip1 : kMelTrip0 + kMelTrip1 + kMelTrip2;
+            const int lo = tb->mel_lo[32 * s + lane];
+            const bool dead = tb->mel_dead[32 * s + lane] != 0;
+            float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;
+  #pragma unroll
+            for (int p = 0; p < trips; ++p) {
+              const float w = tb->mel_w[(toff + p) * 32 + lane];
+              e0 = fmaf(w, fbuf[lo + p], e0);
+              e1 = fmaf(w, fbuf[kPowStride + lo + p], e1);
+              e2 = fmaf(w, fbuf[2 * kFftHalf + lo + p], e2);
+              e3 = fmaf(w, fbuf[2 * kFftHalf + kPowStride + lo + p], e3);
+            }
+            const float e[4] = {e0, e1, e2, e3};
+  #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float d = 3.0102999566398120f * env.log2(fmaxf(e[j], 1e-10f));   // 10 log10(max(x, amin))
+              const bool live = !dead && (m0 + j) < nFm;
+              env.push(live && d < cand_p, clist, ncand, kClampCap, ((m0 + j - mf_begin) << 7) | (32 * s + lane), d);
+              if (live) {
+                dmax[li] = fmaxf(dmax[li], d);
+                dmin[li] = fminf(dmin[li], d);
+                d = fmaxf(d, thr);
+              }
+              db[j][s] = d;
+            }
+          });
+  #pragma unroll
+          for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
+          const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
+          static_for<0, kDctQuads>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const float4 q = dq[i * 32 + lane];
+            const float qc[4] = {q.x, q.y, q.z, q.w};
+            static_for<0, 4>([&](auto cc) {
+              constexpr int c = decltype(cc)::value;
+              constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(db[j][s], qc[c], share[li][j * kMfcc + k]);
+            });
+          });
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          (void)li;
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int v = lane + 32 * half;
+            if (v < 52) {
+              float a = 0.0f;
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) a += fbuf[v * 33 + j];
+              const int fr = m0 + v / kMfcc;
+              if (fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = a;
+            }
+          }
+        });
+        env.wsync();
+      }
+    const int ops[2] = {kOpMax, kOpMin};
+    block_reduce<2>(env, wred, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
+    if (pass == 1) break;
+    const float dbmax = (float)rout[0], dbmin = (float)rout[1];
+    if (ncand > kClampCap) env.lanes([&](int lane, int li) { (void)li; if (lane == 0) ctr[2] = 1; });
+    if (env.tid == 0) { part->db_max = dbmax; part->db_min = dbmin; part->mf_frames = nfr; }
+    env.csync();                                          // #1: every rank's dB extrema (and this CTA's overflow flag) are visible
+    for (int rr = 0; rr < NR; ++rr) {
+      const Partials* rp = env.remote(part, rr);
+      gmax = fmaxf(gmax, rp->db_max);
+      gmin = fminf(gmin, rp->db_min);
+    }
+    // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  The DCT is linear, so a clamped value only
+    // adds dct[m][k] * (thr - dB) to its frame: every warp patches the frames it produced from its own
+    // candidate list (a frame belongs to exactly one warp; list order is program order: deterministic).
+    // A list that overflowed (long digital silence inside a loud segment) redoes this CTA's pass clamped.
+    thr = gmax - 80.0f;
+    fix = (P.parts & kPartMfcc) && (dbmin < thr);
+    slow = fix && ctr[2] != 0;
+    if (!slow) break;
   }
-  // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  The DCT is linear, so a clamped value only
-  // adds dct[m][k] * (thr - dB) to its frame: every warp patches the frames it produced from its own
-  // candidate list (a frame belongs to exactly one warp; list order is program order: deterministic).
-  // A list that overflowed (long digital silence inside a loud segment) redoes this CTA's pass clamped.
-  const float thr = gmax - 80.0f;
-  const bool fix = (P.parts & kPartMfcc) && (dbmin < thr);
-  const bool slow = fix && ctr[2] != 0;
-  if (slow) {
-    float a, b;
-    int c;
-    mfcc_pass(thr, -3.0e38f, ctr + 1, &c, &a, &b);
-  } else if (fix) {
+  if (fix && !slow) {
     env.lanes([&](int lane, int li) {
       (void)li;
       if (lane < kMfcc) {
@@ -679,8 +697,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         }
       }
     });
-    env.sync();
   }
+  env.sync();
 
   // ---------------------------------------------------------------- MFCC moments (timbre z-score, clarity)
   {

@@ -90,28 +90,36 @@ template <int I, int N, class F> MSA_FN void static_for(F&& f) {
   }
 }
 
-// a * W_32^K  (forward: exp(-2 pi i K / 32); inverse: conjugate), K = 0..15
-template <int K, bool INV> MSA_FN c32 mul_w32(c32 a) {
-  if constexpr (K == 0) {
-    return a;
-  } else if constexpr (K == 8) {
-    return rot90<INV>(a);
-  } else if constexpr (K == 4) {
-    constexpr float h = 0.70710678118654752440f;
-    return INV ? c32{(a.x - a.y) * h, (a.x + a.y) * h} : c32{(a.x + a.y) * h, (a.y - a.x) * h};
-  } else if constexpr (K == 12) {
-    constexpr float h = 0.70710678118654752440f;
-    return INV ? c32{(-a.x - a.y) * h, (a.x - a.y) * h} : c32{(a.y - a.x) * h, -(a.x + a.y) * h};
-  } else {
-    constexpr float c = cospi16<K>(), s = sinpi16<K>();        // angle = pi K / 16
-    // forward w = (c, -s): (a.x c + a.y s, a.y c - a.x s); inverse w = (c, s)
-    return INV ? c32{a.x * c - a.y * s, a.y * c + a.x * s} : c32{a.x * c + a.y * s, a.y * c - a.x * s};
-  }
-}
-
 template <bool INV> MSA_FN void dft4(c32& a, c32& b, c32& c, c32& d) {
   c32 t0 = a + c, t1 = a - c, t2 = b + d, t3 = rot90<INV>(b - d);
   a = t0 + t2; b = t1 + t3; c = t0 - t2; d = t1 - t3;
+}
+
+// Radix-2 butterfly with the twiddle folded into the multiply-adds:
+//   lo = e + o W_32^K,  hi = e - o W_32^K
+// Generic twiddle: lo costs four FMAs, and hi = 2 e - lo two more (6 instead of 8 instructions);
+// W_32^4 / W_32^12 (45 degrees): two adds and four FMAs; K = 0 and K = 8 are four adds.
+template <int K, bool INV> MSA_FN void bfly(c32 e, c32 o, c32& lo, c32& hi) {
+  if constexpr (K == 0) {
+    lo = e + o; hi = e - o;
+  } else if constexpr (K == 8) {
+    const c32 t = rot90<INV>(o);
+    lo = e + t; hi = e - t;
+  } else if constexpr (K == 4 || K == 12) {
+    constexpr float h = 0.70710678118654752440f;
+    // forward K=4: t = h (o.x + o.y, o.y - o.x); K=12: t = h (o.y - o.x, -(o.x + o.y)); inverse: conjugate twiddle
+    const float s = o.x + o.y, d = o.y - o.x;
+    float tx, ty;                       // t / h
+    if constexpr (K == 4) { tx = INV ? -d : s; ty = INV ? s : d; }
+    else { tx = INV ? -s : d; ty = INV ? -d : -s; }
+    lo = c32{fmaf(h, tx, e.x), fmaf(h, ty, e.y)};
+    hi = c32{fmaf(-h, tx, e.x), fmaf(-h, ty, e.y)};
+  } else {
+    constexpr float c = cospi16<K>(), sn = sinpi16<K>();       // angle = pi K / 16
+    constexpr float s = INV ? -sn : sn;                        // forward w = (c, -sn): t = (o.x c + o.y sn, o.y c - o.x sn)
+    lo = c32{fmaf(o.y, s, fmaf(o.x, c, e.x)), fmaf(-o.x, s, fmaf(o.y, c, e.y))};
+    hi = c32{fmaf(2.0f, e.x, -lo.x), fmaf(2.0f, e.y, -lo.y)};
+  }
 }
 
 // v[k] <- sum_q v[q] W_N^{qk}, radix-2 decimation in time built on dft4 (N = 4, 8, 16, 32)
@@ -126,9 +134,7 @@ template <int N, bool INV> MSA_FN void dft_pow2(c32* v) {
     dft_pow2<N / 2, INV>(o);
     static_for<0, N / 2>([&](auto kc) {
       constexpr int k = decltype(kc)::value;
-      const c32 t = mul_w32<k*(32 / N), INV>(o[k]);
-      v[k] = e[k] + t;
-      v[k + N / 2] = e[k] - t;
+      bfly<k*(32 / N), INV>(e[k], o[k], v[k], v[k + N / 2]);
     });
   }
 }

@@ -86,3 +86,40 @@ def test_shard_ranges_and_row_packing(built):
     rows = pack_rows(torch.randn(5, 31), torch.randn(5, 7), torch.tensor([6, 0, 3, 2, 1]), 1 << 20)
     u = unpack_rows(rows)
     assert u["argmax"].tolist() == [6, 0, 3, 2, 1] and u["segment_id"].tolist() == list(range(1 << 20, (1 << 20) + 5))
+
+
+def _gather_worker(rank, world, port, n_total, out_dir):
+    import os
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import msa_b200  # noqa: F401
+    from msa_b200.pipeline import ROW_WORDS, gather_rows, pack_rows, shard_range, unpack_rows
+    b, e = shard_range(n_total, world, rank)
+    g = torch.Generator().manual_seed(1000)                      # every rank draws the same full table ...
+    full_audio, full_logits = torch.randn(n_total, 31, generator=g), torch.randn(n_total, 7, generator=g)
+    rows = pack_rows(full_audio[b:e], full_logits[b:e], full_logits[b:e].argmax(1), b)   # ... and owns one shard of it
+    table = gather_rows(rows, n_total, world, rank)
+    u = unpack_rows(table)
+    assert table.shape == (n_total, ROW_WORDS)
+    assert torch.equal(u["audio_row"], full_audio) and torch.equal(u["logits"], full_logits)
+    assert u["segment_id"].tolist() == list(range(n_total))
+    assert torch.equal(u["argmax"].long(), full_logits.argmax(1))
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([table.shape[0]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [720, 7, 1])
+def test_sharded_gather_world_size_2_gloo(built, tmp_path, n_total):
+    """contiguous shards, ONE all_gather of the [S/N, 40] result tables (ragged shards
+    padded and trimmed).  Two CPU processes over gloo stand in for two GPUs over NCCL."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_gather_worker, args=(2, port, n_total, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(os.path.join(tmp_path, "ok0.npy")) and os.path.exists(os.path.join(tmp_path, "ok1.npy"))
