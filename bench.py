@@ -247,6 +247,26 @@ def run_native(args):
         model.fused_with_argmax(face_dev, feat, text_dev)
     ms_fus = timed(fus_only, args.steps, args.warmup) / args.steps
 
+    # streaming mode (BASELINE configs[4]): 5 s window, 0.5 s hop, one chunk at a time; host-visible latency of
+    # push() = 16 KB upload + feature kernel + fusion chain + read-back of the 7 logits
+    stream = None
+    if rank == 0 and world == 1 and not args.no_streaming:
+        sw = msa_b200.StreamingWindow(ana, model, window=SEG_SAMPLES, hop=8000)
+        chunks = pcm_host[:64].reshape(-1, 8000)
+        face1, text1 = face_dev[0], text_dev[0]
+        lat = []
+        for i in range(args.stream_chunks + 20):
+            t0 = time.perf_counter()
+            out = sw.push(chunks[i % chunks.shape[0]], face1, text1)
+            if out is not None:
+                out["fused_emotion"].cpu()
+            torch.cuda.synchronize()
+            if i >= 20:
+                lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        stream = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "chunks": len(lat),
+                  "window_s": 5.0, "hop_s": 0.5, "timing": "host perf_counter around StreamingWindow.push + logits read-back"}
+
     if rank == 0:
         audio_s = S * SEG_SECONDS * world
         value = audio_s * args.steps / (ms_total / 1000.0)
@@ -273,6 +293,7 @@ def run_native(args):
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(pcm_host.numel() * 2 + face_host.numel() * 4 + text_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(rows_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps, "input": "int16 PCM from pinned host memory",
                     "pipeline": f"SegmentPipeline.run_host: {args.chunk}-segment chunks, upload overlapped with compute"},
+            "stream_latency": stream,
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }
@@ -288,8 +309,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--segments", type=int, default=1024)
-    ap.add_argument("--chunk", type=int, default=256, help="segments per upload chunk of the host-buffer (e2e) path")
+    ap.add_argument("--chunk", type=int, default=128, help="segments per upload chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--stream-chunks", type=int, default=500)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

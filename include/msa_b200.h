@@ -45,8 +45,9 @@ extern "C" {
 int msa_version(void);
 const char* msa_strerror(int code);
 
-/* Smallest number of CTAs per cluster that can hold a segment of T samples (0 if T is unsupported;
- * a 5 s segment needs 1), and the dynamic shared memory per CTA.  With cluster_size = 0 the launch
+/* Number of CTAs per cluster used for a segment of T samples: the smallest that lets two CTAs share an
+ * SM, else the smallest that fits at all (0 if T is unsupported; a 5 s segment needs 1; the limit is
+ * about 3 minutes), and the dynamic shared memory per CTA.  With cluster_size = 0 the launch
  * uses this value for large batches and up to 8 CTAs per segment when B is small (streaming). */
 int msa_features_cluster_size(int T);
 int msa_features_smem_bytes(int T, int cluster_size);

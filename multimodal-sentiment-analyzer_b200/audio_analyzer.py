@@ -115,6 +115,18 @@ class AudioAnalyzer:
         feat, detail, _ = self._run(w, self._emo(w.shape[0], emotion_probs), _lib.PART_ALL)
         return (feat, detail) if return_detail else feat
 
+    def analyze_into(self, waveforms: torch.Tensor, out_rows: torch.Tensor, emotion_probs: Optional[torch.Tensor] = None) -> None:
+        """``analyze_batch`` writing the [B, 31] rows into a caller-owned contiguous buffer (no detail record,
+        no allocation): the chunked host-buffer pipeline fills one row table slice by slice."""
+        B, T = waveforms.shape
+        if (not waveforms.is_contiguous() or not out_rows.is_contiguous() or out_rows.shape != (B, 31)
+                or out_rows.dtype != torch.float32 or waveforms.dtype not in (torch.int16, torch.float32)):
+            raise ValueError("analyze_into needs contiguous [B, T] int16/fp32 waves and a contiguous fp32 [B, 31] output")
+        fn = self._lib.msa_features_s16 if waveforms.dtype == torch.int16 else self._lib.msa_features_f32
+        rc = fn(_lib.ptr(waveforms), B, T, _lib.ptr(self._emo(B, emotion_probs)), _lib.ptr(out_rows), None, None, self._flags(),
+                _lib.PART_ALL, 0, _lib.current_stream_ptr(self.device))
+        _lib.check(rc, "msa_features")
+
     # ------------------------------------------------------------------ reference API
     def analyze(self, audio_path: str, speaker_id: str) -> AudioAnalysis:
         """audio_analyzer.py:56-150: load, resample to 16 kHz, all features, LayerNorm(31), slices."""

@@ -58,11 +58,14 @@ int feat_threads() {
   return t;
 }
 
-// Smallest cluster whose per-CTA shared-memory layout fits (the per-segment MFCC tile and the energy
-// atoms are split over the ranks; everything else is per warp).
+// Smallest cluster whose per-CTA shared-memory layout lets two CTAs share an SM, else the smallest that
+// fits at all (the per-segment MFCC tile and the energy atoms are split over the ranks; everything else
+// is per warp).
 int features_cluster_size(int T) {
   if (T < 1) return 0;
   const int nwarps = feat_threads() / 32;
+  for (int c = 1; c <= 8; c *= 2)                       // two CTAs per SM hide each other's serial phases
+    if (feat_layout(T, c, nwarps).total <= kHalfSmem) return c;
   for (int c = 1; c <= 8; c *= 2)
     if (feat_layout(T, c, nwarps).total <= kMaxSmem) return c;
   return 0;

@@ -122,11 +122,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Up to three independent layers of the same shape class (the per-modality branches of fusion_model.py:44-86)
+// share one launch: blockIdx.z selects the layer.
+struct TcBatch {
+  CUtensorMap maps[3][4];   // A_hi, A_lo, W_hi, W_lo
+  TcEpilogue ep[3];
+};
+
 // kPair: 2-CTA cluster along grid.y (n_total = 1024). kFinal: fuse Linear(512 -> 7) + argmax.
 template <bool kPair, bool kFinal>
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_linear_ln_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                    const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, const TcEpilogue ep) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __grid_constant__ TcBatch batch) {
+  const CUtensorMap& tmA_hi = batch.maps[blockIdx.z][0];
+  const CUtensorMap& tmA_lo = batch.maps[blockIdx.z][1];
+  const CUtensorMap& tmW_hi = batch.maps[blockIdx.z][2];
+  const CUtensorMap& tmW_lo = batch.maps[blockIdx.z][3];
+  const TcEpilogue& ep = batch.ep[blockIdx.z];
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcTail* tail = reinterpret_cast<TcTail*>(smem + kStages * kStageBytes);
@@ -440,34 +450,41 @@ struct LayerLaunch {
   bool final_layer;
 };
 
-static int launch_layer(const LayerLaunch& L, int B, int Bp, const unsigned char* packed, const PackedHeader& h, float* logits,
-                        int32_t* argmax, cudaStream_t s) {
-  const GemmWeight& gw = kGemmWeights[L.gemm];
-  CUtensorMap mA_hi, mA_lo, mW_hi, mW_lo;
-  int rc;
-  if ((rc = make_map(&mA_hi, L.a_hi, Bp, L.a_cols, BLOCK_M))) return rc;
-  if ((rc = make_map(&mA_lo, L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
-  if ((rc = make_map(&mW_hi, packed + h.hi_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
-  if ((rc = make_map(&mW_lo, packed + h.lo_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
-  TcEpilogue ep{};
-  ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
-  ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
-  ep.beta = reinterpret_cast<const float*>(packed + h.f32_off[L.beta_t]);
-  ep.out_hi = static_cast<__nv_bfloat16*>(L.out_hi);
-  ep.out_lo = static_cast<__nv_bfloat16*>(L.out_lo);
-  ep.ld_out = L.ld_out;
-  ep.col_off = L.col_off;
-  ep.n_total = gw.N;
-  ep.m_valid = B;
-  ep.k_blocks = gw.Kpad / BLOCK_K;
-  ep.w8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_W]);
-  ep.b8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_B]);
-  ep.logits = logits;
-  ep.argmax = argmax;
+// One launch for `count` (1..3) layers of the same output width (all 1024-wide or all 512-wide).
+static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const unsigned char* packed, const PackedHeader& h,
+                         float* logits, int32_t* argmax, cudaStream_t s) {
+  TcBatch batch;
+  std::memset(&batch, 0, sizeof(batch));
+  const int N = kGemmWeights[Ls[0].gemm].N;
+  for (int i = 0; i < count; ++i) {
+    const LayerLaunch& L = Ls[i];
+    const GemmWeight& gw = kGemmWeights[L.gemm];
+    if (gw.N != N || L.final_layer != Ls[0].final_layer) return MSA_ERR_BAD_ARGUMENT;
+    int rc;
+    if ((rc = make_map(&batch.maps[i][0], L.a_hi, Bp, L.a_cols, BLOCK_M))) return rc;
+    if ((rc = make_map(&batch.maps[i][1], L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
+    if ((rc = make_map(&batch.maps[i][2], packed + h.hi_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
+    if ((rc = make_map(&batch.maps[i][3], packed + h.lo_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
+    TcEpilogue& ep = batch.ep[i];
+    ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
+    ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
+    ep.beta = reinterpret_cast<const float*>(packed + h.f32_off[L.beta_t]);
+    ep.out_hi = static_cast<__nv_bfloat16*>(L.out_hi);
+    ep.out_lo = static_cast<__nv_bfloat16*>(L.out_lo);
+    ep.ld_out = L.ld_out;
+    ep.col_off = L.col_off;
+    ep.n_total = gw.N;
+    ep.m_valid = B;
+    ep.k_blocks = gw.Kpad / BLOCK_K;
+    ep.w8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_W]);
+    ep.b8 = reinterpret_cast<const float*>(packed + h.f32_off[T_FUS8_B]);
+    ep.logits = logits;
+    ep.argmax = argmax;
+  }
 
-  const bool pair = gw.N == 1024;
+  const bool pair = N == 1024;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(Bp / BLOCK_M, gw.N / N_CTA, 1);
+  cfg.gridDim = dim3(Bp / BLOCK_M, N / N_CTA, count);
   cfg.blockDim = dim3(kTcThreads, 1, 1);
   cfg.dynamicSmemBytes = kTcSmemBytes;
   cfg.stream = s;
@@ -481,13 +498,13 @@ static int launch_layer(const LayerLaunch& L, int B, int Bp, const unsigned char
   cudaError_t e;
   if (pair) {
     cudaFuncSetAttribute(tc_linear_ln_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<true, false>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
-  } else if (L.final_layer) {
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<true, false>, batch);
+  } else if (Ls[0].final_layer) {
     cudaFuncSetAttribute(tc_linear_ln_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, true>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, true>, batch);
   } else {
     cudaFuncSetAttribute(tc_linear_ln_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, false>, mA_hi, mA_lo, mW_hi, mW_lo, ep);
+    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, false>, batch);
   }
   if (e != cudaSuccess) return (int)e;
   note_launches(1);
@@ -524,17 +541,19 @@ int fusion_forward_tc(const float* face, const float* audio, const float* text, 
   const int p3_g[3] = {G_FACE_P3, G_AUDIO_P3, G_TEXT_P3}, p3_b[3] = {T_FACE_P3_B, T_AUDIO_P3_B, T_TEXT_P3_B};
   const int l4w[3] = {T_FACE_P4_W, T_AUDIO_P4_W, T_TEXT_P4_W}, l4b[3] = {T_FACE_P4_B, T_AUDIO_P4_B, T_TEXT_P4_B};
   int rc;
+  // the modality branches are independent: all projections in one launch, all processors in the next
+  LayerLaunch proj[3], proc[3];
   for (int m = 0; m < pa.nmod; ++m) {
-    LayerLaunch p{bf(xin_hi[m]), bf(xin_lo[m]), xk[m], proj_g[m], proj_b[m], l0w[m], l0b[m], bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, 0, false};
-    if ((rc = launch_layer(p, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
-    LayerLaunch q{bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, p3_g[m], p3_b[m], l4w[m], l4b[m], bf(wl.cat_hi), bf(wl.cat_lo), cat_w, m * kHalf, false};
-    if ((rc = launch_layer(q, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+    proj[m] = LayerLaunch{bf(xin_hi[m]), bf(xin_lo[m]), xk[m], proj_g[m], proj_b[m], l0w[m], l0b[m], bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, 0, false};
+    proc[m] = LayerLaunch{bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, p3_g[m], p3_b[m], l4w[m], l4b[m], bf(wl.cat_hi), bf(wl.cat_lo), cat_w, m * kHalf, false};
   }
+  if ((rc = launch_layers(proj, pa.nmod, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  if ((rc = launch_layers(proc, pa.nmod, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
   LayerLaunch f0{bf(wl.cat_hi), bf(wl.cat_lo), cat_w, three ? G_FUS0 : G_FUS2, three ? T_FUS0_B : T_FUS2_B, T_FUS1_W, T_FUS1_B,
                  bf(wl.f1_hi), bf(wl.f1_lo), kHidden, 0, false};
-  if ((rc = launch_layer(f0, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  if ((rc = launch_layers(&f0, 1, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
   LayerLaunch f4{bf(wl.f1_hi), bf(wl.f1_lo), kHidden, G_FUS4, T_FUS4_B, T_FUS5_W, T_FUS5_B, nullptr, nullptr, 0, 0, true};
-  if ((rc = launch_layer(f4, B, Bp, packed, h, logits7, argmax, s))) return rc;
+  if ((rc = launch_layers(&f4, 1, B, Bp, packed, h, logits7, argmax, s))) return rc;
   return (int)cudaGetLastError();
 }
 

@@ -97,51 +97,60 @@ class SegmentPipeline:
 
     @torch.no_grad()
     def run_host(self, pcm_host: torch.Tensor, face_host: torch.Tensor, text_host: Optional[torch.Tensor],
-                 rows_host: torch.Tensor, first_id: int = 0, chunk: int = 256) -> torch.Tensor:
-        """Same as ``run`` for HOST buffers (pinned: int16 PCM [n, T], face [n, 27], text [n, 783] or None):
-        the batch is cut into chunks of `chunk` segments; a copy stream uploads chunk i+1 into the other
-        half of a double buffer while the compute stream runs the two kernels on chunk i, and the
-        [n, 40] result table comes back with one device->host copy into `rows_host` (pinned).  The
-        returned device table and `rows_host` are valid once the current stream has been synchronised."""
+                 rows_host: torch.Tensor, first_id: int = 0, chunk: int = 128) -> torch.Tensor:
+        """Same as ``run`` for HOST buffers (pinned: int16 PCM [n, T], face [n, 27], text [n, 783] or None).
+        The PCM is cut into chunks of `chunk` segments: a copy stream uploads chunk i+1 into the other half of
+        a double buffer while the compute stream runs the feature kernel on chunk i (the upload is the
+        longer of the two: 160 KB per segment over PCIe).  The face / text rows go up once, the fusion chain
+        runs once over all n rows when the last chunk's features are done, and the [n, 40] result table comes
+        back with one device->host copy into `rows_host` (pinned).  The returned device table and `rows_host`
+        are valid once the current stream has been synchronised."""
         n, T = pcm_host.shape
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         st = self._host_state(chunk, T, text_host is not None, n)
         copy_s = st["copy_stream"]
-        copy_s.wait_stream(cur)
-        rows = st["rows"][:n]
+        copy_s.wait_stream(cur)                                   # buffers of the previous call are free
+        audio_rows = st["audio"][:n]
         n_chunks = (n + chunk - 1) // chunk
+        side = None
         for i in range(n_chunks):
             b, e = i * chunk, min(n, (i + 1) * chunk)
             k = i & 1
             with torch.cuda.stream(copy_s):
                 if st["free"][k] is not None:
-                    copy_s.wait_event(st["free"][k])              # the kernels that read this half are done
+                    copy_s.wait_event(st["free"][k])              # the kernel that read this half is done
                 st["pcm"][k][: e - b].copy_(pcm_host[b:e], non_blocking=True)
-                st["face"][k][: e - b].copy_(face_host[b:e], non_blocking=True)
-                if text_host is not None:
-                    st["text"][k][: e - b].copy_(text_host[b:e], non_blocking=True)
                 up = torch.cuda.Event()
                 up.record(copy_s)
+                if i == 0:                                        # small side inputs ride behind the first chunk
+                    st["face"][:n].copy_(face_host, non_blocking=True)
+                    if text_host is not None:
+                        st["text"][:n].copy_(text_host, non_blocking=True)
+                    side = torch.cuda.Event()
+                    side.record(copy_s)
             cur.wait_event(up)
-            text = st["text"][k][: e - b] if text_host is not None else None
-            rows[b:e] = self.run(st["pcm"][k][: e - b], st["face"][k][: e - b], text, None, first_id + b)
+            self.analyzer.analyze_into(st["pcm"][k][: e - b], audio_rows[b:e])
             done = torch.cuda.Event()
             done.record(cur)
             st["free"][k] = done
+        cur.wait_event(side)
+        text = st["text"][:n] if text_host is not None else None
+        logits, amax = self.fusion.fused_with_argmax(st["face"][:n], audio_rows, text)
+        rows = pack_rows(audio_rows, logits, amax, first_id)
         rows_host[:n].copy_(rows, non_blocking=True)
         return rows
 
     def _host_state(self, chunk: int, T: int, with_text: bool, n: int):
         key = (chunk, T, with_text)
         st = getattr(self, "_hs", None)
-        if st is None or st["key"] != key or st["rows"].shape[0] < n:
+        if st is None or st["key"] != key or st["audio"].shape[0] < n:
             dev = self.device
             st = {"key": key, "copy_stream": torch.cuda.Stream(dev), "free": [None, None],
                   "pcm": [torch.empty(chunk, T, dtype=torch.int16, device=dev) for _ in range(2)],
-                  "face": [torch.empty(chunk, 27, device=dev) for _ in range(2)],
-                  "text": [torch.empty(chunk, 783, device=dev) for _ in range(2)] if with_text else None,
-                  "rows": torch.empty(n, ROW_WORDS, device=dev)}
+                  "face": torch.empty(n, 27, device=dev),
+                  "text": torch.empty(n, 783, device=dev) if with_text else None,
+                  "audio": torch.empty(n, 31, device=dev)}
             self._hs = st
         return st
 
