@@ -79,13 +79,6 @@ struct GpuEnv {
       cnt += __popc(m);
     }
   }
-
-  // dynamic work distribution: one shared-memory counter per CTA, one atomic per warp and task
-  __device__ __forceinline__ int next_task(int* ctr) {
-    int t = 0;
-    if (lane == 0) t = atomicAdd(ctr, 1);
-    return __shfl_sync(0xffffffffu, t, 0);
-  }
 };
 
 }  // namespace msa

@@ -51,7 +51,6 @@ constexpr int kDetailStride = 96;
 constexpr int kRow512 = 33, kRow400 = 25;        // row strides (complex words) of the pass-A -> pass-B tiles
 constexpr int kFftHalf = 16 * kRow512;           // one FFT tile: 528 complex = 4224 bytes
 constexpr int kWarpBufBytes = 2 * kFftHalf * 8;  // two tiles per warp
-constexpr int kTailFloats = 3 * kHopP;           // the 3 hop-blocks a quad leaves to its successor
 constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
 constexpr int kRedSlots = 16;
 constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
@@ -86,7 +85,7 @@ struct Partials {
 };
 
 struct FeatLayout {
-  int buf_off, tail_off, mfl_off, atoms_off, tab_off, wred_off, out_off, part_off, ctr_off;
+  int buf_off, mfl_off, atoms_off, tab_off, wred_off, out_off, part_off, ctr_off;
   int mfl_frames, atoms_cap, total;
 };
 
@@ -117,10 +116,10 @@ FeatLayout feat_layout(int T, int nranks, int nwarps) {
   const int gather = (T / kAtom + 8) * 4;                      // rank 0 gathers all energy atoms there at the end
   if (buf < gather) buf = gather;
   l.buf_off = take(buf);
-  // the overlap-add tails ("pitch" phase) and the MFCC rows (written after it) share one region
-  int tm = (nwarps + 1) * kTailFloats * 4;
-  if (tm < l.mfl_frames * kMfcc * 4) tm = l.mfl_frames * kMfcc * 4;
-  l.tail_off = l.mfl_off = take(tm);
+  // the MFCC rows share their region with the "pitch" phase's per-warp copy of the quad's input samples
+  int mx = l.mfl_frames * kMfcc * 4;
+  if (mx < nwarps * 4 * kHopP * 4) mx = nwarps * 4 * kHopP * 4;
+  l.mfl_off = take(mx);
   l.atoms_off = take(l.atoms_cap * 4);
   l.tab_off = take((int)sizeof(SmemTables));
   l.wred_off = take(kRedSlots * nwarps * 8);
@@ -193,7 +192,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
   double* wred = reinterpret_cast<double*>(smem + lay.wred_off);
-  float* tails = reinterpret_cast<float*>(smem + lay.tail_off);
   float* mfl = reinterpret_cast<float*>(smem + lay.mfl_off);
   float* atoms = reinterpret_cast<float*>(smem + lay.atoms_off);
   const SmemTables* tb = reinterpret_cast<const SmemTables*>(smem + lay.tab_off);
@@ -212,7 +210,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   // ---------------------------------------------------------------- stage the constant tables
   env.copy16(smem + lay.tab_off, &P.tab->s, (int)sizeof(SmemTables));
-  if (env.warp == 0) env.lanes([&](int lane, int li) { (void)li; if (lane < 4) ctr[lane] = 0; });   // task counters of the two MFCC passes, overflow flag
+  if (env.warp == 0) env.lanes([&](int lane, int li) { (void)li; if (lane < 4) ctr[lane] = 0; });   // ctr[2]: candidate-list overflow flag
   env.sync();
 
   // ---------------------------------------------------------------- K1: energy atoms, totals
@@ -313,109 +311,109 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int qper = ceil_div(nQ, NR);
       const int q_begin = (r * qper < nQ) ? r * qper : nQ;
       const int q_end = (q_begin + qper < nQ) ? q_begin + qper : nQ;
-      const int q_first = (q_begin > 0) ? q_begin - 1 : 0;      // warm-up quad: only its tail is used
-      const int ntasks = (q_end > q_begin) ? q_end - q_first : 0;
-      const int niter = ceil_div(ntasks, NW);
+      // every warp owns a contiguous run of this rank's quads and carries the overlap-add tail of a quad
+      // (hop-blocks 4..6, which the next quad starts with) in registers: no barrier, no shared-memory
+      // exchange, and consecutive quads of a warp re-read overlapping samples from L1.  The quad before the
+      // run is computed as a warm-up (only its tail is used).
+      const int wper = ceil_div(q_end - q_begin, NW);
+      const int wq_lo = q_begin + env.warp * wper;
+      const int wq_begin = (wq_lo < q_end) ? wq_lo : q_end;
+      const int wq_end = (wq_begin + wper < q_end) ? wq_begin + wper : q_end;
+      const int wq_first = (wq_begin > 0 && wq_begin < wq_end) ? wq_begin - 1 : wq_begin;
       float own[S][7][4];
-      float xv[S][4][4];                                           // the input samples the quad's 4 own blocks are compared with
-      for (int it = 0; it < niter; ++it) {
-        const int task = it * NW + env.warp;
-        const bool active = task < ntasks;
-        const int quad = q_first + task;
+      for (int i = 0; i < S; ++i)
+        for (int b = 0; b < 7; ++b)
+          for (int j = 0; j < 4; ++j) own[i][b][j] = 0.0f;
+      // the 512 input samples the quad's own hop-blocks are compared with: pass A has them in registers,
+      // every lane parks its 16 in shared memory (lane-private slots, no synchronisation) until the end of the quad
+      float* xs = reinterpret_cast<float*>(smem + lay.mfl_off) + env.warp * (4 * kHopP);
+      for (int it = 0; it <= wper; ++it) {
+        // the barrier is not needed for correctness: it keeps the warps of the CTA in the same code region
+        // (the loop body is ~100 KB of SASS; warps drifting apart thrash the instruction cache)
+#ifndef MSA_NO_LOCKSTEP
+        env.sync();
+#endif
+        const int quad = wq_begin - 1 + it;
+        if (quad < wq_first || quad >= wq_end) continue;
         const int f0 = 4 * quad;
         const int s0 = kHopP * f0 - kNfftP / 2;                  // first sample of frame f0
-        if (active) {
-          const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
-          // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples
-          for (int h = 0; h < 2; ++h) {
-            env.lanes([&](int lane, int li) {
-              (void)li;
-              const int sb = s0 + 2 * h * kHopP;
-              const bool oka = (f0 + 2 * h) < nFp, okb = (f0 + 2 * h + 1) < nFp;
-              float raw[20];
-              if (interior) {
-#pragma unroll
-                for (int i = 0; i < 20; ++i) raw[i] = env.ld(x + sb + 32 * i + lane);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 20; ++i) raw[i] = xr(sb + 32 * i + lane);
-              }
-              c32 z[16];
-#pragma unroll
-              for (int n1 = 0; n1 < 16; ++n1) {
-                const float w = tb->win512[32 * n1 + lane];
-                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
-              }
-              pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
-            });
-          }
-          env.wsync();
-          // pass B forward = the STFT spectrum X[k1 + 16 k2] of this row; phase_vocoder(rate = 1.0)
-          // returns its input, so the inverse radix-32 follows in the same registers
+        const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
+        // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples
+        for (int h = 0; h < 2; ++h) {
           env.lanes([&](int lane, int li) {
             (void)li;
-            c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow512;
-            c32 v[32];
+            const int sb = s0 + 2 * h * kHopP;
+            const bool oka = (f0 + 2 * h) < nFp, okb = (f0 + 2 * h + 1) < nFp;
+            float raw[20];
+            if (interior) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = row[i];
-            dft32<false>(v);
-            dft32<true>(v);
+              for (int i = 0; i < 20; ++i) raw[i] = env.ld(x + sb + 32 * i + lane);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) row[i] = v[i];
+              for (int i = 0; i < 20; ++i) raw[i] = xr(sb + 32 * i + lane);
+            }
+            if (h == 0) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) xs[32 * i + lane] = raw[i];
+            }
+            c32 z[16];
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) {
+              const float w = tb->win512[32 * n1 + lane];
+              z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
+            }
+            pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
           });
-          env.wsync();
-          // inverse pass A, synthesis window (x 1/512), overlap-add of the quad's 4 frames in registers:
-          // frame f0 + j covers hop-blocks j .. j+3 of the quad's 7 blocks
-          env.lanes([&](int lane, int li) {
-#pragma unroll
-            for (int b = 0; b < 7; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) own[li][b][i] = 0.0f;
-          });
-          for (int h = 0; h < 2; ++h) {
-            env.lanes([&](int lane, int li) {
-              c32 z[16];
-              pass_a_inv<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
-              static_for<0, 16>([&](auto nc) {
-                constexpr int n1 = decltype(nc)::value;
-                const float w = tb->win512[32 * n1 + lane];    // the 1/512 of the unnormalised inverse lives in ienv
-                if (h == 0) {
-                  own[li][n1 / 4][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4][n1 % 4]);
-                  own[li][n1 / 4 + 1][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 1][n1 % 4]);
-                } else {
-                  own[li][n1 / 4 + 2][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4 + 2][n1 % 4]);
-                  own[li][n1 / 4 + 3][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 3][n1 % 4]);
-                }
-              });
-            });
-          }
-          // blocks 4..6 overlap the next quad: slot w+1 holds the tail of the quad warp w just did
-          env.lanes([&](int lane, int li) {
-            float* t = tails + (env.warp + 1) * kTailFloats;
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) t[b * kHopP + 32 * i + lane] = own[li][4 + b][i];
-          });
-          // issue the loads of the comparison samples now: their latency hides behind the barrier
-          if (quad >= q_begin) {
-            env.lanes([&](int lane, int li) {
-#pragma unroll
-              for (int b = 0; b < 4; ++b)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  const int t = kHopP * (f0 + b) + 32 * i + lane - kNfftP / 2;
-                  xv[li][b][i] = (t >= 0 && t < T) ? env.ld(x + t) : 0.0f;
-                }
-            });
-          }
         }
-        env.sync();
-        if (active && quad >= q_begin) {
-          // finalise blocks 0..3 of the quad: add the predecessor's tail, divide by the window envelope,
-          // compare with the input (torch.istft trims the n_fft/2 padding: t = position - 256)
-          const bool has_prev = quad > 0;
-          const float* pt = tails + env.warp * kTailFloats;      // slot 0 = last warp of the previous iteration
+        env.wsync();
+        // pass B forward = the STFT spectrum X[k1 + 16 k2] of this row; phase_vocoder(rate = 1.0)
+        // returns its input, so the inverse radix-32 follows in the same registers
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow512;
+          c32 v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = row[i];
+          dft32<false>(v);
+          dft32<true>(v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) row[i] = v[i];
+        });
+        env.wsync();
+        // inverse pass A, synthesis window, overlap-add of the quad's 4 frames in registers: frame f0 + j
+        // covers hop-blocks j .. j+3 of the quad's 7 blocks; blocks 0..2 start from the predecessor's tail
+        env.lanes([&](int lane, int li) {
+          (void)lane;
+#pragma unroll
+          for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) own[li][b][i] = own[li][4 + b][i];
+#pragma unroll
+          for (int b = 3; b < 7; ++b)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) own[li][b][i] = 0.0f;
+        });
+        for (int h = 0; h < 2; ++h) {
+          env.lanes([&](int lane, int li) {
+            c32 z[16];
+            pass_a_inv<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
+            static_for<0, 16>([&](auto nc) {
+              constexpr int n1 = decltype(nc)::value;
+              const float w = tb->win512[32 * n1 + lane];    // the 1/512 of the unnormalised inverse lives in ienv
+              if (h == 0) {
+                own[li][n1 / 4][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4][n1 % 4]);
+                own[li][n1 / 4 + 1][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 1][n1 % 4]);
+              } else {
+                own[li][n1 / 4 + 2][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4 + 2][n1 % 4]);
+                own[li][n1 / 4 + 3][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 3][n1 % 4]);
+              }
+            });
+          });
+        }
+        env.wsync();                                             // the tiles are free for the next quad
+        if (quad >= wq_begin) {
+          // finalise blocks 0..3 of the quad: divide by the window envelope and compare with the input
+          // (torch.istft trims the n_fft/2 padding: t = position - 256)
           const int b0 = 4 * quad;
           const bool fast = (b0 >= 3) && (b0 + 3 <= nFp - 1) && (kHopP * (b0 + 4) - kNfftP / 2 <= T);
           env.lanes([&](int lane, int li) {
@@ -427,10 +425,9 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               for (int i = 0; i < 4; ++i) {
                 const int o = 32 * i + lane;
                 const int t = kHopP * (b0 + b) + o - kNfftP / 2;
-                float y = own[li][b][i];
-                if (b < 3 && has_prev) y += pt[b * kHopP + o];
+                const float y = own[li][b][i];
                 if (fast) {
-                  const float pv = fabsf(xv[li][b][i] - y * tb->ienv[o]);
+                  const float pv = fabsf(xs[kHopP * b + o] - y * tb->ienv[o]);
                   s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
                 } else if (t >= 0 && t < T) {
                   float e = 0.0f;
@@ -439,7 +436,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                     const int f = b0 + b - j;
                     if (f >= 0 && f < nFp) { const float w = tb->win512[j * kHopP + o]; e = fmaf(w, w, e); }
                   }
-                  const float pv = fabsf(xv[li][b][i] - y / (e * (float)kNfftP));
+                  const float pv = fabsf(xs[kHopP * b + o] - y / (e * (float)kNfftP));
                   s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
                 }
               }
@@ -447,17 +444,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
             pmax[li] = fmaxf(pmax[li], mx);
           });
         }
-        env.sync();
-        if (active && env.warp == NW - 1) {
-          env.lanes([&](int lane, int li) {
-#pragma unroll
-            for (int b = 0; b < 3; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) tails[b * kHopP + 32 * i + lane] = own[li][4 + b][i];
-          });
-        }
       }
-      env.sync();
     }
     const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
     block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
@@ -502,16 +489,18 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   bool fix = false, slow = false;
   for (int pass = 0; pass < 2; ++pass) {
     const float cand_p = (pass == 0) ? cand : -3.0e38f;
-    int* counter = ctr + pass;
       float dmax[S], dmin[S];
       for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
       float pw[S][28];
       float share[S][52];
       float* fbuf = reinterpret_cast<float*>(wbuf);
+      // a contiguous run of quads per warp (adjacent quads share a hop of samples in L1)
       const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
-      for (;;) {
-        const int task = env.next_task(counter);
-        if (task >= ntasks) break;
+      const int tper = ceil_div(ntasks, NW);
+      const int t_lo = env.warp * tper;
+      const int t_begin = (t_lo < ntasks) ? t_lo : ntasks;
+      const int t_end = (t_begin + tper < ntasks) ? t_begin + tper : ntasks;
+      for (int task = t_begin; task < t_end; ++task) {
         const int m0 = 4 * (mq_begin + task);
         const int s0 = kHopM * m0 - kNfftM / 2;
         const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);

@@ -65,7 +65,6 @@ struct CpuEnv {
     if (cnt < cap) { int bits; std::memcpy(&bits, &val, 4); list[cnt] = int2{key, bits}; }
     ++cnt;
   }
-  int next_task(int* ctr) { return __atomic_fetch_add(ctr, 1, __ATOMIC_RELAXED); }
 };
 
 }  // namespace msa
