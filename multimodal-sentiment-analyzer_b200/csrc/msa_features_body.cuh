@@ -374,10 +374,13 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           c32 v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = row[i];
-          dft32<false>(v);
-          dft32<true>(v);
+          // the unnormalised inverse DFT is the forward DFT read backwards (y[n] = DFT(X)[(32 - n) mod 32]),
+          // so both directions run the same code (one rolled loop: half the instruction-cache footprint)
+          // and the index reversal is applied once, as register renaming, when the row is written back
+#pragma unroll 1
+          for (int rep = 0; rep < 2; ++rep) dft32<false>(v);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) row[i] = v[i];
+          for (int i = 0; i < 32; ++i) row[i] = v[(32 - i) & 31];
         });
         env.wsync();
         // inverse pass A, synthesis window, overlap-add of the quad's 4 frames in registers: frame f0 + j
@@ -770,8 +773,10 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     if (env.tid == 0) {
       const double NaN = nan("");
       Partials tot = *part;
+#pragma unroll 1
       for (int rr = 1; rr < NR; ++rr) {
         const Partials* rp = env.remote(part, rr);
+#pragma unroll 1
         for (int k = 0; k < kMfcc; ++k) tot.mf_sum[k] += rp->mf_sum[k];
         tot.mf_sumsq += rp->mf_sumsq; tot.mf_abs_lo += rp->mf_abs_lo; tot.mf_abs_hi += rp->mf_abs_hi;
         tot.p_n += rp->p_n; tot.p_sum += rp->p_sum; tot.p_sumsq += rp->p_sumsq;
@@ -779,8 +784,10 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         tot.p_max = fmaxf(tot.p_max, rp->p_max);
         tot.mf_frames += rp->mf_frames;
       }
-      float raw[27];
+      // cold, once-per-segment code: arrays in shared memory and rolled loops keep it out of the instruction cache's way
+      float* raw = reinterpret_cast<float*>(wred);
       const float* emo = P.emo8 ? P.emo8 + (size_t)seg * 8 : nullptr;
+#pragma unroll 1
       for (int k = 0; k < 8; ++k) raw[k] = emo ? emo[k] : 0.125f;
       // pitch: mean of the z-scored residual. mu and sigma are fp32 tensors in the reference, so the
       // value is the rounding residue of mu; the residual itself is fp32 FFT noise (~1e-8).
@@ -804,14 +811,17 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         const double n = (double)tot.mf_frames * kMfcc;
         if (tot.mf_frames > 0) {
           double ssum = 0.0;
+#pragma unroll 1
           for (int k = 0; k < kMfcc; ++k) ssum += tot.mf_sum[k];
           const double mu = ssum / n;
           const double var = (n > 1.0) ? (tot.mf_sumsq - ssum * mu) / (n - 1.0) : NaN;
           const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : NaN));
+#pragma unroll 1
           for (int k = 0; k < kMfcc; ++k) raw[10 + k] = (float)((tot.mf_sum[k] / tot.mf_frames - mu) / (sd + 1e-6));
           const double hi_m = tot.mf_abs_hi / (7.0 * tot.mf_frames), lo_m = tot.mf_abs_lo / (6.0 * tot.mf_frames);
           clarity = py_clip01((double)((float)hi_m / ((float)lo_m + 1e-6f)));
         } else {
+#pragma unroll 1
           for (int k = 0; k < kMfcc; ++k) raw[10 + k] = 0.0f;
         }
       }
@@ -846,19 +856,23 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const float q4[4] = {(float)quality, (float)snr, (float)clarity, (float)consistency};
 
       // AudioFeatureNormalizer: pad 27 -> 31 with zeros, LayerNorm(31) (gamma 1, beta 0, eps 1e-5, biased var)
-      float ln[31];
+      float* ln = raw + 32;
       {
         double m = 0.0;
+#pragma unroll 1
         for (int k = 0; k < 27; ++k) m += (double)raw[k];
         m /= 31.0;
         double v = 0.0;
+#pragma unroll 1
         for (int k = 0; k < 31; ++k) { const double d = ((k < 27) ? (double)raw[k] : 0.0) - m; v += d * d; }
         v /= 31.0;
         const double rs = 1.0 / sqrt(v + 1e-5);
+#pragma unroll 1
         for (int k = 0; k < 31; ++k) ln[k] = (float)((((k < 27) ? (double)raw[k] : 0.0) - m) * rs);
       }
       // fusion input row: LN slices ++ quality, torch.nan_to_num(nan=0.0) (+-inf -> +-FLT_MAX)
       float* out = P.feat31 + (size_t)seg * 31;
+#pragma unroll 1
       for (int k = 0; k < 31; ++k) {
         float v = (k < 27) ? ln[k] : q4[k - 27];
         if (v != v) v = 0.0f;
@@ -868,15 +882,19 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       }
       if (P.detail) {
         float* d = P.detail + (size_t)seg * kDetailStride;
+#pragma unroll 1
         for (int k = 0; k < 27; ++k) d[k] = raw[k];
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) d[27 + k] = q4[k];
         d[31] = 0.0f;
+#pragma unroll 1
         for (int k = 0; k < 31; ++k) d[32 + k] = ln[k];
         d[63] = 0.0f;
         d[64] = gmax; d[65] = (float)p_mean; d[66] = (float)p_std; d[67] = tot.p_max;
         d[68] = (float)tot.e_total; d[69] = (float)tot.e_noise; d[70] = (float)tot.mf_frames; d[71] = (float)nG;
         d[72] = (float)tot.p_n; d[73] = (float)nBk; d[74] = (float)nA;
         d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
+#pragma unroll 1
         for (int k = 79; k < kDetailStride; ++k) d[k] = 0.0f;
       }
     }
