@@ -117,6 +117,33 @@ int msa_fusion_set_impl(int impl);
 int msa_aggregate_speakers(const int32_t* label, const int32_t* speaker, int S, int n_speakers, int32_t* hist,
                            int32_t* dominant, int32_t* run3, void* stream);
 
+/* ---- PCM ingest: resample to the analyzer's rate (src/analyzers/audio_analyzer.py:74-77) ------- */
+
+/* torchaudio.transforms.Resample(orig_freq, new_freq) with its defaults (sinc_interp_hann, lowpass_filter_width 6,
+ * rolloff 0.99): x [B, length] fp32 (or int16 PCM, scaled by 1/32768 like torchaudio.load) -> y [B, out_length]
+ * fp32 with out_length = msa_resample_out_len(length, orig_freq, new_freq) = ceil(new * length / orig).
+ * Rate pairs whose reduced filter (2 * width + orig/gcd taps) does not fit one CTA's staging buffer return
+ * MSA_ERR_UNSUPPORTED_LENGTH (every common audio rate to 16 kHz fits). */
+int msa_resample_out_len(int length, int orig_freq, int new_freq);
+int msa_resample_f32(const float* x, int B, int length, int orig_freq, int new_freq, float* y, int out_length, void* stream);
+int msa_resample_s16(const int16_t* pcm, int B, int length, int orig_freq, int new_freq, float* y, int out_length, void* stream);
+/* The polyphase filter bank the two calls above use, built on the HOST ([phases][taps] like torchaudio's
+ * `Resample.kernel`); kernel_out may be NULL to query the sizes.  No device needed (tests, capacity planning). */
+int msa_resample_kernel_host(int orig_freq, int new_freq, float* kernel_out, int capacity, int* width, int* taps, int* phases);
+
+/* ---- feature-row normalisation (src/utils/normalization.py:19-98) ------------------------------ */
+
+/* {Face,Text,Audio}FeatureNormalizer.normalize for B rows: x [B, d_in] (row stride ld_in) is zero-padded or
+ * truncated to target_dim (27 / 783 / 31) and LayerNorm'ed (biased variance, eps 1e-5 in the reference; gamma /
+ * beta [target_dim] or NULL = the untrained 1 / 0) into y [B, target_dim] (row stride ld_out).
+ * flags & 1: torch.nan_to_num(nan=0) on the result (streaming_processor.py:293-300). */
+#define MSA_ROWS_NAN_TO_NUM 1
+int msa_rows_layernorm(const float* x, int B, int d_in, int ld_in, int target_dim, const float* gamma, const float* beta,
+                       float eps, float* y, int ld_out, int flags, void* stream);
+
+/* torch.nan_to_num(x, nan=0.0) in place over n contiguous floats (row assembly, streaming_processor.py:293-300). */
+int msa_nan_to_num(float* x, long long n, void* stream);
+
 /* Number of kernel launches the last call of each kind issued on this thread (bench accounting). */
 int msa_last_launch_count(void);
 

@@ -9,10 +9,13 @@ include/msa_b200.h (libmsa_b200.so, loaded with ctypes).  There is no CPU fallba
 works anywhere, but any compute call without the built library and a CUDA device raises.
 """
 from .structures import AudioAnalysis, DictMixin
-from .audio_analyzer import AudioAnalyzer, AudioFeatureNormalizer
+from .audio_analyzer import AudioAnalyzer
+from .ingest import (AudioFeatureNormalizer, FaceFeatureNormalizer, FeatureNormalizer, TextFeatureNormalizer, assemble_row,
+                     resample)
 from .fusion_model import AdvancedFusionModel, FusionModel
 from .pipeline import SegmentPipeline, aggregate_speakers, shard_range
 from .streaming import StreamingWindow
 
-__all__ = ["AudioAnalysis", "DictMixin", "AudioAnalyzer", "AudioFeatureNormalizer", "AdvancedFusionModel",
+__all__ = ["AudioAnalysis", "DictMixin", "AudioAnalyzer", "AudioFeatureNormalizer", "FaceFeatureNormalizer", "TextFeatureNormalizer", "FeatureNormalizer", "assemble_row",
+           "resample", "AdvancedFusionModel",
            "FusionModel", "SegmentPipeline", "aggregate_speakers", "shard_range", "StreamingWindow"]

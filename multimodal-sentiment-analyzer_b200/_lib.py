@@ -30,6 +30,12 @@ _SIGNATURES = {
     "msa_fusion_pack": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "msa_fusion_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "msa_fusion_set_impl": (c_int, [c_int]),
+    "msa_resample_out_len": (c_int, [c_int, c_int, c_int]),
+    "msa_resample_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "msa_resample_s16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "msa_resample_kernel_host": (c_int, [c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
+    "msa_rows_layernorm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, ctypes.c_float, c_void_p, c_int, c_int, c_void_p]),
+    "msa_nan_to_num": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),
     "msa_aggregate_speakers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -30,24 +30,7 @@ logger = logging.getLogger(__name__)
 _RAW = slice(0, 27)
 
 
-class AudioFeatureNormalizer:
-    """Attribute-compatible stand-in for src/utils/normalization.py:19-44 (pad/truncate to 31, then
-    an untrained LayerNorm(31)).  Inside ``analyze`` the LayerNorm is fused into the feature kernel;
-    this object only serves callers that use ``analyzer.normalizer.normalize(t)`` directly."""
-
-    def __init__(self, device):
-        self.target_dim = 8 + 1 + 1 + 13 + 1 + 3 + 4
-        self.device = device
-
-    def normalize(self, tensor: torch.Tensor) -> torch.Tensor:
-        if tensor.dim() == 1:
-            tensor = tensor.unsqueeze(0)
-        n = tensor.shape[1]
-        if n < self.target_dim:
-            tensor = torch.cat([tensor, torch.zeros(tensor.shape[0], self.target_dim - n, device=tensor.device)], dim=1)
-        elif n > self.target_dim:
-            tensor = tensor[:, :self.target_dim]
-        return torch.nn.functional.layer_norm(tensor, (self.target_dim,), eps=1e-5)
+from .ingest import AudioFeatureNormalizer, resample  # noqa: E402  (normalization.py:19-44; audio_analyzer.py:74-77)
 
 
 class AudioAnalyzer:
@@ -134,10 +117,8 @@ class AudioAnalyzer:
             pcm, sr, channels = _read_wav(audio_path)
             if channels != 1:
                 raise ValueError("multi-channel audio makes the reference's torch.cat fail (falls to the default analysis)")
-            if sr != self.sample_rate:
-                import torchaudio
-                w = torch.from_numpy(pcm.astype(np.float32) / 32768.0)[None, :]
-                w = torchaudio.functional.resample(w, sr, self.sample_rate).to(self.device).contiguous()
+            if sr != self.sample_rate:                                                # audio_analyzer.py:74-77
+                w = resample(torch.from_numpy(pcm)[None, :].to(self.device), sr, self.sample_rate).contiguous()
             else:
                 w = torch.from_numpy(pcm)[None, :].to(self.device).contiguous()      # int16 PCM ingest
             _, detail, _ = self._run(w, self._emo(1, None), _lib.PART_ALL)
