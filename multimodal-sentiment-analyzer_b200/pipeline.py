@@ -112,10 +112,14 @@ class SegmentPipeline:
         copy_s = st["copy_stream"]
         copy_s.wait_stream(cur)                                   # buffers of the previous call are free
         audio_rows = st["audio"][:n]
-        n_chunks = (n + chunk - 1) // chunk
+        # chunk boundaries; the last chunk is cut short so that little compute is left once the upload ends
+        bounds = list(range(0, n, chunk)) + [n]
+        tail = max(1, chunk // 4)
+        if bounds[-1] - bounds[-2] > tail:
+            bounds.insert(-1, n - tail)
         side = None
-        for i in range(n_chunks):
-            b, e = i * chunk, min(n, (i + 1) * chunk)
+        for i in range(len(bounds) - 1):
+            b, e = bounds[i], bounds[i + 1]
             k = i & 1
             with torch.cuda.stream(copy_s):
                 if st["free"][k] is not None:
