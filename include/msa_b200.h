@@ -141,6 +141,23 @@ int msa_resample_kernel_host(int orig_freq, int new_freq, float* kernel_out, int
 int msa_rows_layernorm(const float* x, int B, int d_in, int ld_in, int target_dim, const float* gamma, const float* beta,
                        float eps, float* y, int ld_out, int flags, void* stream);
 
+/* ---- additive descriptors (north-star vocabulary; NOT computed by the reference) ---------- */
+
+/* Real f0 track and frame-level voicing of B mono segments of T samples (16 kHz):
+ *   lags   [B, msa_pitch_frames(T)]  int32 out: best NCCF lag per 10 ms frame (torchaudio _find_max_per_frame)
+ *   f0     [B, msa_pitch_outputs(T)] fp32 out: 16000 / lower-median-of-30(lags) = torchaudio.functional.
+ *          detect_pitch_frequency(waveform, 16000) with its defaults
+ *   voiced [B, msa_voiced_frames(T)] int32 out or NULL: 400/160 frame energy > 0.1 * mean frame energy, the
+ *          frame-level analogue of audio_analyzer.py:223-228
+ * The oracle for these is the restated torchaudio algorithm (oracle/descriptors_np.py), not the reference. */
+int msa_pitch_frames(int T);
+int msa_pitch_outputs(int T);
+int msa_voiced_frames(int T);
+int msa_pitch_track_f32(const float* wav, int B, int T, int32_t* lags, float* f0, int32_t* voiced, void* stream);
+int msa_pitch_track_s16(const int16_t* pcm, int B, int T, int32_t* lags, float* f0, int32_t* voiced, void* stream);
+/* probs [B,7] = softmax(logits [B,7]) (fusion_model.py:94 returns raw logits; consumers argmax them). */
+int msa_softmax7(const float* logits, int B, float* probs, void* stream);
+
 /* torch.nan_to_num(x, nan=0.0) in place over n contiguous floats (row assembly, streaming_processor.py:293-300). */
 int msa_nan_to_num(float* x, long long n, void* stream);
 

@@ -35,6 +35,12 @@ _SIGNATURES = {
     "msa_resample_s16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "msa_resample_kernel_host": (c_int, [c_int, c_int, c_void_p, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)]),
     "msa_rows_layernorm": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, ctypes.c_float, c_void_p, c_int, c_int, c_void_p]),
+    "msa_pitch_frames": (c_int, [c_int]),
+    "msa_pitch_outputs": (c_int, [c_int]),
+    "msa_voiced_frames": (c_int, [c_int]),
+    "msa_pitch_track_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msa_pitch_track_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msa_softmax7": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "msa_nan_to_num": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),
     "msa_aggregate_speakers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -110,6 +110,25 @@ class AudioAnalyzer:
                 _lib.PART_ALL, 0, _lib.current_stream_ptr(self.device))
         _lib.check(rc, "msa_features")
 
+    def track_pitch(self, waveforms: torch.Tensor, with_voicing: bool = True):
+        """Additive output (NOT computed by the reference): a real f0 track per segment,
+        = torchaudio.functional.detect_pitch_frequency(waveform, 16000), the raw best lag per 10 ms frame and
+        frame-level voicing flags.  waveforms [B, T] fp32 / int16 on the device ->
+        {"f0": [B, n_frames - 15] Hz, "lags": [B, n_frames] int32, "voiced": [B, (T - 400) // 160 + 1] int32}."""
+        w = waveforms.to(self.device)
+        if w.dtype != torch.int16:
+            w = w.float()
+        w = w.contiguous()
+        B, T = w.shape
+        lib = self._lib
+        lags = torch.empty(B, lib.msa_pitch_frames(T), device=self.device, dtype=torch.int32)
+        f0 = torch.empty(B, lib.msa_pitch_outputs(T), device=self.device, dtype=torch.float32)
+        voiced = torch.empty(B, lib.msa_voiced_frames(T), device=self.device, dtype=torch.int32) if with_voicing else None
+        fn = lib.msa_pitch_track_s16 if w.dtype == torch.int16 else lib.msa_pitch_track_f32
+        _lib.check(fn(_lib.ptr(w), B, T, _lib.ptr(lags), _lib.ptr(f0), _lib.ptr(voiced), _lib.current_stream_ptr(self.device)),
+                   "msa_pitch_track")
+        return {"f0": f0, "lags": lags, "voiced": voiced}
+
     # ------------------------------------------------------------------ reference API
     def analyze(self, audio_path: str, speaker_id: str) -> AudioAnalysis:
         """audio_analyzer.py:56-150: load, resample to 16 kHz, all features, LayerNorm(31), slices."""

@@ -134,6 +134,14 @@ class AdvancedFusionModel(nn.Module):
         """Additive batched entry point: (logits [B,7], argmax [B] int32) in one call."""
         return self._device_forward(face, audio, text, want_argmax=True)
 
+    def class_probs(self, logits: torch.Tensor) -> torch.Tensor:
+        """Additive output: softmax over the 7 classes of the "fused" logits (the reference returns raw logits,
+        fusion_model.py:94, and its consumers argmax them)."""
+        x = logits.to(self.device).float().reshape(-1, 7).contiguous()
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().msa_softmax7(_lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.current_stream_ptr(self.device)), "msa_softmax7")
+        return out.reshape(logits.shape)
+
     # ------------------------------------------------------------------ reference API
     def forward(self, face_probs: Optional[torch.Tensor] = None, audio_probs: Optional[torch.Tensor] = None,
                 text_probs: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
