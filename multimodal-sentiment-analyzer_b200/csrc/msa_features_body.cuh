@@ -53,6 +53,7 @@ constexpr int kFftHalf = 16 * kRow512;           // one FFT tile: 528 complex = 
 constexpr int kWarpBufBytes = 2 * kFftHalf * 8;  // two tiles per warp
 constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
 constexpr int kRedSlots = 16;
+constexpr int kK1Groups = 2;                     // load groups in flight per warp in the wave-statistics phase (160 floats of scratch each; 4 in flight measured no faster)
 constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
 constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (the largest MFCC use of a warp's buffer)
 // top_db candidates of one warp live behind the transpose tile: 198 entries of (frame << 7 | filter, dB)
@@ -231,20 +232,20 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
       n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
       float* scr = reinterpret_cast<float*>(wbuf);
-      // two groups (10 float4 per lane) are in flight per step: this phase is pure load latency
-      for (int gp = g0 + 2 * env.warp; gp < g1; gp += 2 * NW) {
-        const int ng = (gp + 1 < g1) ? 2 : 1;
+      // kK1Groups groups (5 float4 per lane each) are in flight per step: this phase is pure load latency
+      for (int gp = g0 + kK1Groups * env.warp; gp < g1; gp += kK1Groups * NW) {
+        const int ng = (g1 - gp < kK1Groups) ? g1 - gp : kK1Groups;
         env.lanes([&](int lane, int li) {
-          float v[2][5][4];
+          float v[kK1Groups][5][4];
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+          for (int u = 0; u < kK1Groups; ++u)
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
               if (u < ng) env.ld4(x, (gp + u) * kGroup + 128 * j + 4 * lane, T, v[u][j]);
               else v[u][j][0] = v[u][j][1] = v[u][j][2] = v[u][j][3] = 0.0f;
             }
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
+          for (int u = 0; u < kK1Groups; ++u) {
             float acc = 0.0f;
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
