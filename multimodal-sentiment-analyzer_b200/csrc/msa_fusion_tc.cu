@@ -7,12 +7,15 @@
 // so each product is issued as three bf16 MMAs with fp32 accumulation in tensor memory:
 //   X W^T ~= Xhi Whi^T + Xlo Whi^T + Xhi Wlo^T      (relative error ~2^-16)
 //
-// Kernel shape: one CTA owns 128 rows x 512 output columns = the whole 128-lane x 512-column
-// tensor memory, so the LayerNorm statistics of a 512-wide layer are thread-local in the
-// epilogue (thread <-> TMEM lane <-> row).  1024-wide layers run as a 2-CTA cluster (one half of
-// the columns each) that exchanges per-row (sum, sum of squares) through distributed shared
-// memory.  Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue.  Operands are staged by TMA into 128-byte-swizzled K-major tiles.
+// Kernel shape: one CTA owns 128 rows x NC output columns in tensor memory (thread <-> TMEM lane <-> row in the
+// epilogue), and the N / NC CTAs that share a row block form a cluster which exchanges the per-row LayerNorm
+// statistics (sum, sum of squares) - and, in the last layer, the partial 7 logits - through distributed shared
+// memory, always summed in rank order so every CTA sees the same bits.
+//   NC = 512 (cluster 1 or 2): large batches; an activation tile is loaded once per 512 columns.
+//   NC = 128 (cluster 4 or 8): small batches (streaming, the 1024-segment step): four times as many CTAs, each
+//                              with a quarter of the MMA chain, because a layer's latency is one CTA's MMA time.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
+// Operands are staged by TMA into 128-byte-swizzled K-major tiles.
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -27,23 +30,31 @@
 namespace msa {
 namespace cg = cooperative_groups;
 
-constexpr int BLOCK_M = 128, BLOCK_K = 64, N_SUB = 256, N_CTA = 512;
-constexpr int kStages = 2;
+constexpr int BLOCK_M = 128, BLOCK_K = 64;
 constexpr int kTileA = BLOCK_M * BLOCK_K * 2;            // 16 KB
-constexpr int kTileW = N_SUB * BLOCK_K * 2;              // 32 KB
-constexpr int kStageBytes = 2 * kTileA + 2 * kTileW;     // 96 KB: A_hi, A_lo, W_hi, W_lo
 constexpr int kTcThreads = 256;
+constexpr int kSmallBatchRows = 4096;                    // at or below: 128 columns per CTA
 constexpr uint32_t kSpinLimit = 400u * 1000u * 1000u;    // a lost barrier traps instead of hanging the GPU
 
+// per-variant shapes: NC columns per CTA, issued in MMAs of NSUB columns
+template <int NC> struct TcShape {
+  static constexpr int kNSub = NC >= 256 ? 256 : NC;
+  static constexpr int kTileW = kNSub * BLOCK_K * 2;                 // 32 KB or 16 KB
+  static constexpr int kStageBytes = 2 * kTileA + 2 * kTileW;        // A_hi, A_lo, W_hi, W_lo: 96 KB or 64 KB
+  static constexpr int kStages = NC >= 256 ? 2 : 3;
+};
+constexpr int kMaxStages = 3;
+
 struct TcTail {            // smem after the stages
-  uint64_t full[kStages], empty[kStages], accum_full;
+  uint64_t full[kMaxStages], empty[kMaxStages], accum_full;
   uint32_t tmem_base, pad;
   float2 stats[BLOCK_M];
-  float bias[N_CTA], gamma[N_CTA], beta[N_CTA];
-  float w8[kOut * N_CTA];  // final layer only
+  float part7[BLOCK_M][8]; // last layer, cluster > 1: this CTA's share of the 7 logits per row
+  float bias[512], gamma[512], beta[512];
+  float w8[kOut * 512];    // final layer only
   float b8[8];
 };
-constexpr int kTcSmemBytes = kStages * kStageBytes + (int)sizeof(TcTail) + 1024;
+template <int NC> constexpr int tc_smem_bytes() { return TcShape<NC>::kStages * TcShape<NC>::kStageBytes + (int)sizeof(TcTail) + 1024; }
 
 struct TcEpilogue {
   const float* bias;       // [n_total]
@@ -129,9 +140,12 @@ struct TcBatch {
   TcEpilogue ep[3];
 };
 
-// kPair: 2-CTA cluster along grid.y (n_total = 1024). kFinal: fuse Linear(512 -> 7) + argmax.
-template <bool kPair, bool kFinal>
+// NC: output columns per CTA (512 or 128); CL: CTAs per cluster along grid.y = n_total / NC;
+// kFinal: fuse Linear(512 -> 7) + argmax behind the ReLU.
+template <int NC, int CL, bool kFinal>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __grid_constant__ TcBatch batch) {
+  using Sh = TcShape<NC>;
+  constexpr int N_SUB = Sh::kNSub, kTileW = Sh::kTileW, kStageBytes = Sh::kStageBytes, kStages = Sh::kStages;
   const CUtensorMap& tmA_hi = batch.maps[blockIdx.z][0];
   const CUtensorMap& tmA_lo = batch.maps[blockIdx.z][1];
   const CUtensorMap& tmW_hi = batch.maps[blockIdx.z][2];
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
   TcTail* tail = reinterpret_cast<TcTail*>(smem + kStages * kStageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * N_CTA;
+  const int n0 = blockIdx.y * NC;
   const int k_blocks = ep.k_blocks;
 
   if (threadIdx.x == 0) {
@@ -151,7 +165,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&tail->tmem_base)), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&tail->tmem_base)), "r"(NC));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int ns = 0; ns < N_CTA / N_SUB; ++ns) {
+      for (int ns = 0; ns < NC / N_SUB; ++ns) {
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&tail->empty[stage], phase ^ 1);
           unsigned char* st = smem + stage * kStageBytes;
@@ -181,11 +195,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      // kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = 256
+      // kind::f16: D fp32, A/B bf16, both K-major, M = 128, N = N_SUB
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_SUB >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
-      for (int ns = 0; ns < N_CTA / N_SUB; ++ns) {
+      for (int ns = 0; ns < NC / N_SUB; ++ns) {
         const uint32_t tmem_d = tmem_base + ns * N_SUB;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&tail->full[stage], phase);
@@ -208,17 +222,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue: thread <-> row
+    // ------------------------------------------------------------------ epilogue pass 1: row statistics of this CTA's columns
     const int q = warp & 3;
     const int row_in_tile = q * 32 + lane;
     const int et = threadIdx.x - 128;
-    for (int i = et; i < N_CTA; i += 128) {
+    for (int i = et; i < NC; i += 128) {
       tail->bias[i] = ep.bias[n0 + i];
       tail->gamma[i] = ep.gamma[n0 + i];
       tail->beta[i] = ep.beta[n0 + i];
     }
     if (kFinal) {
-      for (int i = et; i < kOut * N_CTA; i += 128) tail->w8[i] = ep.w8[i];
+      for (int i = et; i < kOut * NC; i += 128) tail->w8[i] = ep.w8[(i / NC) * ep.n_total + n0 + (i % NC)];
       if (et < kOut) tail->b8[et] = ep.b8[et];
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");                       // epilogue warps only
@@ -226,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
     float sum = 0.0f, sumsq = 0.0f;
-    for (int c = 0; c < N_CTA; c += 32) {
+    for (int c = 0; c < NC; c += 32) {
       float v[32];
       tmem_ld32(trow + c, v);
 #pragma unroll
@@ -239,26 +253,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     tail->stats[row_in_tile] = make_float2(sum, sumsq);
   }
 
-  if (kPair) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();                                                      // both halves' row statistics are published
-    if (warp >= 4) {
-      const int row_in_tile = (warp & 3) * 32 + lane;
-      const float2* peer = cluster.map_shared_rank(&tail->stats[0], cluster.block_rank() ^ 1);
+  cg::cluster_group cluster = cg::this_cluster();
+  if (CL > 1) cluster.sync();                                            // every CTA's row statistics are published
+  else __syncthreads();
+  if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue pass 2: normalise, ReLU, store / project
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    float2 tot = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < CL; ++r) {                                       // rank order: every CTA adds the same bits
+      const float2* peer = (CL > 1) ? cluster.map_shared_rank(&tail->stats[0], r) : &tail->stats[0];
       const float2 o = peer[row_in_tile];
-      float2 mine = tail->stats[row_in_tile];
-      mine.x += o.x;
-      mine.y += o.y;
-      // merged statistics stay in registers (stats[] is not overwritten: the peer may still be reading it)
-      const float mean = mine.x / (float)ep.n_total;
-      const float var = fmaxf(mine.y / (float)ep.n_total - mean * mean, 0.0f);
-      const float rstd = rsqrtf(var + 1e-5f);
-      // second pass
-      const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      const int row = m0 + row_in_tile;
-      for (int c = 0; c < N_CTA; c += 32) {
-        float v[32];
-        tmem_ld32(trow + c, v);
+      tot.x += o.x;
+      tot.y += o.y;
+    }
+    const float mean = tot.x / (float)ep.n_total;
+    const float var = fmaxf(tot.y / (float)ep.n_total - mean * mean, 0.0f);
+    const float rstd = rsqrtf(var + 1e-5f);
+    const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int row = m0 + row_in_tile;
+    float acc[kOut];
+#pragma unroll
+    for (int j = 0; j < kOut; ++j) acc[j] = 0.0f;
+    for (int c = 0; c < NC; c += 32) {
+      float v[32];
+      tmem_ld32(trow + c, v);
+      if (kFinal) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float y = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
+          y = fmaxf(y, 0.0f);
+#pragma unroll
+          for (int j = 0; j < kOut; ++j) acc[j] = fmaf(y, tail->w8[j * NC + c + i], acc[j]);
+        }
+      } else {
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -283,57 +311,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    cluster.sync();                                                      // the peer has finished reading my statistics
-  } else {
-    if (warp >= 4) {
-      const int row_in_tile = (warp & 3) * 32 + lane;
-      const float2 mine = tail->stats[row_in_tile];
-      const float mean = mine.x / (float)ep.n_total;
-      const float var = fmaxf(mine.y / (float)ep.n_total - mean * mean, 0.0f);
-      const float rstd = rsqrtf(var + 1e-5f);
-      const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-      const int row = m0 + row_in_tile;
-      float acc[kOut];
+    if (kFinal) {
+      if (CL > 1) {
 #pragma unroll
-      for (int j = 0; j < kOut; ++j) acc[j] = 0.0f;
-      for (int c = 0; c < N_CTA; c += 32) {
-        float v[32];
-        tmem_ld32(trow + c, v);
-        if (kFinal) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float y = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
-            y = fmaxf(y, 0.0f);
-#pragma unroll
-            for (int j = 0; j < kOut; ++j) acc[j] = fmaf(y, tail->w8[j * N_CTA + c + i], acc[j]);
-          }
-        } else {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float y0 = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
-            float y1 = (v[i + 1] + tail->bias[c + i + 1] - mean) * rstd * tail->gamma[c + i + 1] + tail->beta[c + i + 1];
-            y0 = fmaxf(y0, 0.0f);
-            y1 = fmaxf(y1, 0.0f);
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-            hi[i / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lo[i / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-          }
-          if (row < ep.m_valid) {
-            const size_t o = (size_t)row * ep.ld_out + ep.col_off + n0 + c;
-            uint4* ph = reinterpret_cast<uint4*>(ep.out_hi + o);
-            uint4* pl = reinterpret_cast<uint4*>(ep.out_lo + o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              ph[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              pl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-        }
-      }
-      if (kFinal && row < ep.m_valid) {
+        for (int j = 0; j < kOut; ++j) tail->part7[row_in_tile][j] = acc[j];
+      } else if (row < ep.m_valid) {
         int best = 0;
         float bv = 0.0f;
 #pragma unroll
@@ -345,12 +327,40 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
         if (ep.argmax) ep.argmax[row] = best;
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
   }
+  if (kFinal && CL > 1) {
+    cluster.sync();                                                      // every CTA's share of the logits is published
+    if (warp >= 4 && cluster.block_rank() == 0) {
+      const int row_in_tile = (warp & 3) * 32 + lane;
+      const int row = m0 + row_in_tile;
+      if (row < ep.m_valid) {
+        float l[kOut];
+#pragma unroll
+        for (int j = 0; j < kOut; ++j) l[j] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) {
+          const float* peer = cluster.map_shared_rank(&tail->part7[0][0], r) + row_in_tile * 8;
+#pragma unroll
+          for (int j = 0; j < kOut; ++j) l[j] += peer[j];
+        }
+        int best = 0;
+        float bv = 0.0f;
+#pragma unroll
+        for (int j = 0; j < kOut; ++j) {
+          l[j] += tail->b8[j];
+          ep.logits[(size_t)row * kOut + j] = l[j];
+          if (j == 0 || l[j] > bv) { bv = l[j]; best = j; }
+        }
+        if (ep.argmax) ep.argmax[row] = best;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CL > 1) cluster.sync();                                            // nobody exits while a peer still reads its smem
+  else __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NC));
   }
 }
 
@@ -450,12 +460,34 @@ struct LayerLaunch {
   bool final_layer;
 };
 
+template <int NC, int CL, bool kFinal>
+static cudaError_t launch_variant(const TcBatch& batch, int Bp, int N, int count, cudaStream_t s) {
+  constexpr int smem = tc_smem_bytes<NC>();
+  cudaError_t e = cudaFuncSetAttribute(tc_linear_ln_kernel<NC, CL, kFinal>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(Bp / BLOCK_M, N / NC, count);
+  cfg.blockDim = dim3(kTcThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = CL;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<NC, CL, kFinal>, batch);
+}
+
 // One launch for `count` (1..3) layers of the same output width (all 1024-wide or all 512-wide).
 static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const unsigned char* packed, const PackedHeader& h,
                          float* logits, int32_t* argmax, cudaStream_t s) {
   TcBatch batch;
   std::memset(&batch, 0, sizeof(batch));
   const int N = kGemmWeights[Ls[0].gemm].N;
+  const bool small = B <= kSmallBatchRows;                       // 128 columns per CTA: more, shorter CTAs
+  const int nsub = small ? TcShape<128>::kNSub : TcShape<512>::kNSub;
   for (int i = 0; i < count; ++i) {
     const LayerLaunch& L = Ls[i];
     const GemmWeight& gw = kGemmWeights[L.gemm];
@@ -463,8 +495,8 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     int rc;
     if ((rc = make_map(&batch.maps[i][0], L.a_hi, Bp, L.a_cols, BLOCK_M))) return rc;
     if ((rc = make_map(&batch.maps[i][1], L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
-    if ((rc = make_map(&batch.maps[i][2], packed + h.hi_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
-    if ((rc = make_map(&batch.maps[i][3], packed + h.lo_off[L.gemm], gw.N, gw.Kpad, N_SUB))) return rc;
+    if ((rc = make_map(&batch.maps[i][2], packed + h.hi_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
+    if ((rc = make_map(&batch.maps[i][3], packed + h.lo_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
     TcEpilogue& ep = batch.ep[i];
     ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
     ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
@@ -481,30 +513,16 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     ep.logits = logits;
     ep.argmax = argmax;
   }
-
-  const bool pair = N == 1024;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(Bp / BLOCK_M, N / N_CTA, count);
-  cfg.blockDim = dim3(kTcThreads, 1, 1);
-  cfg.dynamicSmemBytes = kTcSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = pair ? 2 : 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  const bool fin = Ls[0].final_layer;
   cudaError_t e;
-  if (pair) {
-    cudaFuncSetAttribute(tc_linear_ln_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<true, false>, batch);
-  } else if (Ls[0].final_layer) {
-    cudaFuncSetAttribute(tc_linear_ln_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, true>, batch);
+  if (N == 1024) {
+    if (fin) return MSA_ERR_BAD_ARGUMENT;
+    e = small ? launch_variant<128, 8, false>(batch, Bp, N, count, s) : launch_variant<512, 2, false>(batch, Bp, N, count, s);
+  } else if (N == 512) {
+    if (fin) e = small ? launch_variant<128, 4, true>(batch, Bp, N, count, s) : launch_variant<512, 1, true>(batch, Bp, N, count, s);
+    else e = small ? launch_variant<128, 4, false>(batch, Bp, N, count, s) : launch_variant<512, 1, false>(batch, Bp, N, count, s);
   } else {
-    cudaFuncSetAttribute(tc_linear_ln_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
-    e = cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<false, false>, batch);
+    return MSA_ERR_BAD_ARGUMENT;
   }
   if (e != cudaSuccess) return (int)e;
   note_launches(1);

@@ -116,9 +116,16 @@ def test_full_size_fusion_batch_65536():
     assert np.abs(got - ref).max() < 1e-3, np.abs(got - ref).max()
     assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
     assert torch.equal(at.long(), lt.argmax(1))
+    # batch == loop of rows: bit-identical within a kernel variant (512 columns per CTA above 4096 rows, 128 below:
+    # the LayerNorm statistics are then summed from 4-8 partials instead of 1-2), within rounding across variants
+    big = torch.from_numpy(np.sort(np.random.default_rng(6).choice(n, 5000, replace=False))).to(dev)
+    lb, _ = m0.fused_with_argmax(fd[big].contiguous(), ad[big].contiguous(), td[big].contiguous())
+    assert torch.equal(lb, lt[big])
     sub = torch.from_numpy(np.sort(idx[:300])).to(dev)
     ls, _ = m0.fused_with_argmax(fd[sub].contiguous(), ad[sub].contiguous(), td[sub].contiguous())
-    assert torch.equal(ls, lt[sub])                                                      # batch == loop of rows
+    assert (ls - lt[sub]).abs().max().item() < 2e-5
+    l1, _ = m0.fused_with_argmax(fd[sub[:7]].contiguous(), ad[sub[:7]].contiguous(), td[sub[:7]].contiguous())
+    assert torch.equal(l1, ls[:7])
     m1, _ = _model(True, 1)
     l1, _ = m1.fused_with_argmax(fd, ad, td)
     torch.cuda.synchronize()
