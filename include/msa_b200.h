@@ -161,6 +161,11 @@ int msa_softmax7(const float* logits, int B, float* probs, void* stream);
 /* torch.nan_to_num(x, nan=0.0) in place over n contiguous floats (row assembly, streaming_processor.py:293-300). */
 int msa_nan_to_num(float* x, long long n, void* stream);
 
+/* Per-segment result table (the only data that crosses GPUs): rows40 [n, 40] 32-bit words =
+ * audio row 31 | logits 7 | argmax (int32 bits) | segment id first_id + r (int32 bits). */
+int msa_pack_rows(const float* audio31, const float* logits7, const int32_t* argmax, int first_id, int n, float* rows40,
+                  void* stream);
+
 /* Number of kernel launches the last call of each kind issued on this thread (bench accounting). */
 int msa_last_launch_count(void);
 

@@ -41,6 +41,7 @@ _SIGNATURES = {
     "msa_pitch_track_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msa_pitch_track_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msa_softmax7": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
+    "msa_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "msa_nan_to_num": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),
     "msa_aggregate_speakers": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

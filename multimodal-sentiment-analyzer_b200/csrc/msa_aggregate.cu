@@ -42,7 +42,30 @@ __global__ void dominant_kernel(const int32_t* __restrict__ hist, int n_speakers
   dominant[p] = best;          // -1: speaker without segments
 }
 
+// result table row = audio row 31 | logits 7 | argmax | segment id (40 x 32-bit words)
+__global__ void pack_rows_kernel(const float* __restrict__ audio, const float* __restrict__ logits,
+                                 const int32_t* __restrict__ argmax, int first_id, int n, float* __restrict__ rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 40) return;
+  const int r = i / 40, c = i - r * 40;
+  float v;
+  if (c < 31) v = audio[r * 31 + c];
+  else if (c < 38) v = logits[r * 7 + (c - 31)];
+  else v = __int_as_float(c == 38 ? argmax[r] : first_id + r);
+  rows[i] = v;
+}
+
 }  // namespace msa
+
+extern "C" int msa_pack_rows(const float* audio31, const float* logits7, const int32_t* argmax, int first_id, int n, float* rows40,
+                             void* stream) {
+  msa::reset_launches();
+  if (!audio31 || !logits7 || !argmax || !rows40 || n < 0) return MSA_ERR_BAD_ARGUMENT;
+  if (n == 0) return MSA_OK;
+  msa::pack_rows_kernel<<<(n * 40 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(audio31, logits7, argmax, first_id, n, rows40);
+  msa::note_launches(1);
+  return (int)cudaGetLastError();
+}
 
 // label [S] int32 (argmax of the fused logits), speaker [S] int32 in [0, n_speakers)
 // hist [n_speakers, 7] int32 out, dominant [n_speakers] int32 out, run3 [S] int32 out

@@ -130,6 +130,18 @@ class AdvancedFusionModel(nn.Module):
         logits = logits.reshape(*lead, self.output_dim)
         return (logits, amax) if want_argmax else logits
 
+    def forward_into(self, face: torch.Tensor, audio: torch.Tensor, text: Optional[torch.Tensor], logits_out: torch.Tensor,
+                     argmax_out: Optional[torch.Tensor]) -> None:
+        """Allocation-free forward for CUDA-graph capture and tight loops: contiguous fp32 device inputs
+        [B, 27] / [B, 31] / [B, 783] or None, outputs written into caller-owned [B, 7] fp32 and [B] int32.
+        Weights must already be packed (call once outside the capture)."""
+        dev = self.device
+        B = face.shape[0]
+        ws = self._ws(B, dev)
+        rc = _lib.lib().msa_fusion_forward(_lib.ptr(face), _lib.ptr(audio), _lib.ptr(text), B, _lib.ptr(self._packed), _lib.ptr(ws),
+                                           ws.numel(), _lib.ptr(logits_out), _lib.ptr(argmax_out), _lib.current_stream_ptr(dev))
+        _lib.check(rc, "msa_fusion_forward")
+
     def fused_with_argmax(self, face, audio, text=None):
         """Additive batched entry point: (logits [B,7], argmax [B] int32) in one call."""
         return self._device_forward(face, audio, text, want_argmax=True)

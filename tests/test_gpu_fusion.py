@@ -209,21 +209,34 @@ def test_host_buffer_pipeline_equals_resident():
         assert torch.equal(out.view(torch.int32), ref.cpu().view(torch.int32))
 
 
-def test_streaming_window_equals_offline():
+@pytest.mark.parametrize("use_graph,with_text", [(False, False), (True, False), (True, True)])
+def test_streaming_window_equals_offline(use_graph, with_text):
+    """5 s window / 0.5 s hop: every hop equals the offline result of the same 80000 samples (bit for bit), on the
+    eager path and on the CUDA-graph path (one captured graph per ring position, replayed after the ring wraps)."""
     dev = need_gpu()
     import msa_b200
     ana = msa_b200.AudioAnalyzer(device="cuda:0")
     m, _ = _model(True, 0)
-    pcm = synth.segment_pcm(77, 80000 + 3 * 8000)
-    face = torch.from_numpy(synth.face_rows(9, 1)).to(dev)
-    sw = msa_b200.StreamingWindow(ana, m)
+    n_push = 27
+    pcm = synth.segment_pcm(77, 80000 + (n_push - 10) * 8000)
+    faces = torch.from_numpy(synth.face_rows(9, n_push)).to(dev)
+    texts = torch.from_numpy(synth.text_rows(10, n_push)).to(dev)
+    sw = msa_b200.StreamingWindow(ana, m, use_graph=use_graph)
     outs = []
-    for i in range(13):
-        o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), face)
+    for i in range(n_push):
+        o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), faces[i], texts[i] if with_text else None)
+        if o is not None:
+            torch.cuda.synchronize()
+            host = o["host"].clone() if "host" in o else None
+            o = {"audio_row": o["audio_row"].clone(), "fused_emotion": o["fused_emotion"].clone(), "argmax": int(o["argmax"].item()),
+                 "host": host}
         outs.append(o)
     assert all(o is None for o in outs[:9]) and all(o is not None for o in outs[9:])
     for j, o in enumerate(outs[9:]):
+        i = j + 9
         seg = torch.from_numpy(pcm[j * 8000: j * 8000 + 80000].copy())[None].to(dev)
         row = ana.analyze_batch(seg)
-        logits, _ = m.fused_with_argmax(face, row, None)
-        assert torch.equal(o["audio_row"], row[0]) and torch.equal(o["fused_emotion"], logits[0])
+        logits, amax = m.fused_with_argmax(faces[i:i + 1], row, texts[i:i + 1] if with_text else None)
+        assert torch.equal(o["audio_row"], row[0]) and torch.equal(o["fused_emotion"], logits[0]) and o["argmax"] == int(amax[0].item())
+        if o["host"] is not None:
+            assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == o["argmax"]
