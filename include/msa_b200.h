@@ -33,7 +33,6 @@ extern "C" {
 
 /* flags of msa_features_* */
 #define MSA_FEAT_STRICT_NAN 1 /* mono intensity = NaN exactly like audio_analyzer.py:194-196 (default) */
-#define MSA_FEAT_BULK_COPY 2  /* reserved (accepted and ignored): the waveform is no longer staged in shared memory */
 /* parts mask: which feature groups to compute (the rest take the reference's exception defaults) */
 #define MSA_PART_WAVE 1  /* rhythm, speech_rate, snr, consistency */
 #define MSA_PART_MFCC 2  /* timbre, clarity */

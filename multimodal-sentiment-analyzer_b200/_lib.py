@@ -47,7 +47,6 @@ _SIGNATURES = {
 }
 
 FEAT_STRICT_NAN = 1
-FEAT_BULK_COPY = 2
 PART_WAVE, PART_MFCC, PART_PITCH, PART_ALL = 1, 2, 4, 7
 DETAIL_STRIDE = 96
 

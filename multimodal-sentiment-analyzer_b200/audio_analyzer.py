@@ -51,7 +51,7 @@ class AudioAnalyzer:
 
     # ------------------------------------------------------------------ kernel entry
     def _flags(self) -> int:
-        return (_lib.FEAT_STRICT_NAN if self.strict_reference else 0) | _lib.FEAT_BULK_COPY
+        return _lib.FEAT_STRICT_NAN if self.strict_reference else 0
 
     def _run(self, waves: torch.Tensor, emo8: Optional[torch.Tensor], parts: int, want_mfcc: bool = False
              ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:

@@ -76,7 +76,7 @@ int features_cluster_size(int T) {
 static int auto_cluster_size(int B, int T) {
   int c = features_cluster_size(T);
   if (c == 0) return 0;
-  while (c < 8 && (long long)B * c * 2 <= kNumSms) c *= 2;
+  while (c < 8 && (long long)B * c * 2 <= 2 * kNumSms) c *= 2;      // up to two CTAs per SM
   return c;
 }
 

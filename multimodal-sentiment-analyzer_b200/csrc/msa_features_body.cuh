@@ -358,10 +358,18 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               for (int i = 0; i < 16; ++i) xs[32 * i + lane] = raw[i];
             }
             c32 z[16];
+            if (interior) {                                        // an interior quad has four valid frames: no selects
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) {
-              const float w = tb->win512[32 * n1 + lane];
-              z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
+              for (int n1 = 0; n1 < 16; ++n1) {
+                const float w = tb->win512[32 * n1 + lane];
+                z[n1] = c32{w * raw[n1], w * raw[n1 + 4]};
+              }
+            } else {
+#pragma unroll
+              for (int n1 = 0; n1 < 16; ++n1) {
+                const float w = tb->win512[32 * n1 + lane];
+                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
+              }
             }
             pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
           });
@@ -523,10 +531,18 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                 for (int i = 0; i < 24; ++i) raw[i] = xr(sb + 25 * i + lane);
               }
               c32 z[16];
+              if (interior) {
   #pragma unroll
-              for (int n1 = 0; n1 < 16; ++n1) {
-                const float w = tb->win400[25 * n1 + lane];
-                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
+                for (int n1 = 0; n1 < 16; ++n1) {
+                  const float w = tb->win400[25 * n1 + lane];
+                  z[n1] = c32{w * raw[n1], w * raw[n1 + 8]};
+                }
+              } else {
+  #pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                  const float w = tb->win400[25 * n1 + lane];
+                  z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 8] : 0.0f};
+                }
               }
               pass_a_fwd<kRow400>(z, tw400, lane, wbuf + h * kTileM);
             }
