@@ -31,21 +31,16 @@ def shard_range(n_items: int, world_size: int, rank: int) -> Tuple[int, int]:
 
 
 def pack_rows(audio_row: torch.Tensor, logits: torch.Tensor, argmax: torch.Tensor, first_id: int) -> torch.Tensor:
-    """[n, 40] fp32 result table; the two integer columns are stored bit-exactly (int32 viewed as fp32).
-    One kernel on the device (msa_pack_rows); plain tensor indexing for host tensors (tests, gloo)."""
+    """[n, 40] fp32 result table on the device (msa_pack_rows); the two integer columns are stored bit-exactly
+    (int32 viewed as fp32)."""
+    if not audio_row.is_cuda:
+        raise _lib.MsaError("pack_rows needs device tensors (msa_b200 has no CPU path)")
     n = audio_row.shape[0]
     rows = torch.empty(n, ROW_WORDS, device=audio_row.device, dtype=torch.float32)
-    if audio_row.is_cuda:
-        a, l, m = audio_row.float().contiguous(), logits.float().contiguous(), argmax.to(torch.int32).contiguous()
-        rc = _lib.lib().msa_pack_rows(_lib.ptr(a), _lib.ptr(l), _lib.ptr(m), int(first_id), n, _lib.ptr(rows),
-                                      _lib.current_stream_ptr(audio_row.device))
-        _lib.check(rc, "msa_pack_rows")
-        return rows
-    rows[:, 0:31] = audio_row
-    rows[:, 31:38] = logits
-    ints = rows.view(torch.int32)
-    ints[:, 38] = argmax.to(torch.int32)
-    ints[:, 39] = torch.arange(first_id, first_id + n, device=audio_row.device, dtype=torch.int32)
+    a, l, m = audio_row.float().contiguous(), logits.float().contiguous(), argmax.to(torch.int32).contiguous()
+    rc = _lib.lib().msa_pack_rows(_lib.ptr(a), _lib.ptr(l), _lib.ptr(m), int(first_id), n, _lib.ptr(rows),
+                                  _lib.current_stream_ptr(audio_row.device))
+    _lib.check(rc, "msa_pack_rows")
     return rows
 
 

@@ -11,6 +11,18 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _host_table(audio_row, logits, first_id):
+    """The [n, 40] result-table layout (msa_b200.pipeline / msa_pack_rows) built on the host for the CPU tests."""
+    from msa_b200.pipeline import ROW_WORDS
+    n = audio_row.shape[0]
+    rows = torch.empty(n, ROW_WORDS, dtype=torch.float32)
+    rows[:, 0:31], rows[:, 31:38] = audio_row, logits
+    ints = rows.view(torch.int32)
+    ints[:, 38] = logits.argmax(1).to(torch.int32)
+    ints[:, 39] = torch.arange(first_id, first_id + n, dtype=torch.int32)
+    return rows
+
+
 @pytest.fixture(scope="module")
 def built():
     import __graft_entry__ as g
@@ -84,9 +96,11 @@ def test_shard_ranges_and_row_packing(built):
         assert r[0][0] == 0 and r[-1][1] == n and all(r[i][1] == r[i + 1][0] for i in range(w - 1))
         sizes = [e - b for b, e in r]
         assert max(sizes) - min(sizes) <= 1
-    rows = pack_rows(torch.randn(5, 31), torch.randn(5, 7), torch.tensor([6, 0, 3, 2, 1]), 1 << 20)
-    u = unpack_rows(rows)
-    assert u["argmax"].tolist() == [6, 0, 3, 2, 1] and u["segment_id"].tolist() == list(range(1 << 20, (1 << 20) + 5))
+    lg = torch.randn(5, 7)
+    u = unpack_rows(_host_table(torch.randn(5, 31), lg, 1 << 20))
+    assert u["argmax"].tolist() == lg.argmax(1).tolist() and u["segment_id"].tolist() == list(range(1 << 20, (1 << 20) + 5))
+    with pytest.raises(Exception):
+        pack_rows(torch.randn(5, 31), lg, lg.argmax(1), 0)                  # device only: no CPU path in the product
 
 
 def _gather_worker(rank, world, port, n_total, out_dir):
@@ -97,11 +111,11 @@ def _gather_worker(rank, world, port, n_total, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import msa_b200  # noqa: F401
-    from msa_b200.pipeline import ROW_WORDS, gather_rows, pack_rows, shard_range, unpack_rows
+    from msa_b200.pipeline import ROW_WORDS, gather_rows, shard_range, unpack_rows
     b, e = shard_range(n_total, world, rank)
     g = torch.Generator().manual_seed(1000)                      # every rank draws the same full table ...
     full_audio, full_logits = torch.randn(n_total, 31, generator=g), torch.randn(n_total, 7, generator=g)
-    rows = pack_rows(full_audio[b:e], full_logits[b:e], full_logits[b:e].argmax(1), b)   # ... and owns one shard of it
+    rows = _host_table(full_audio[b:e], full_logits[b:e], b)                   # ... and owns one shard of it
     table = gather_rows(rows, n_total, world, rank)
     u = unpack_rows(table)
     assert table.shape == (n_total, ROW_WORDS)
