@@ -10,19 +10,23 @@
 //           segment-level `energy > 0.1 * energy.mean()` (/root/reference/src/analyzers/audio_analyzer.py:223-228).
 //   probs   softmax over the 7 fused logits (fusion_model.py:94 leaves them raw).
 //
-// One CTA per segment, one warp per 10 ms frame: the frame and its 189-sample look-ahead sit in a 352-float
-// shared-memory row; lane l owns the lags 1 + l + 32 q (q < 6), so one broadcast load of s[i] and six
-// conflict-free loads of s[i + lag] feed twelve FMAs (correlation and the energy of the shifted frame).
+// One warp per 10 ms frame (CTAs of 64 frames): the frame and its look-ahead sit in a shared-memory row; lane l
+// owns 7 consecutive lags, so the shifted samples slide through a register window and a step costs two
+// shared-memory loads for 7 FMAs; the energies of the shifted frames come from one fp64 prefix sum per frame.
 // Time-domain on purpose: the direct sums keep the arg-max decisions within rounding distance of torch's.
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "msa_api_internal.h"
 
 namespace msa {
 
-constexpr int kPFrame = 160, kPLags = 189, kPLagMin = 5, kPMedWin = 30, kPRow = 352, kPWarps = 8;
+constexpr int kPFrame = 160, kPLags = 189, kPLagMin = 5, kPMedWin = 30, kPWarps = 8;
+constexpr int kPLpl = 7;                       // lags per lane
+constexpr int kPChunk = 64;                    // frames per CTA of the lag kernel (8 per warp)
+constexpr int kPRow = 416;                     // frame + look-ahead of the last lane's window, rounded to 32
 constexpr int kVWin = 400, kVHop = 160;
 
 __device__ __forceinline__ float pt_load(const float* p) { return __ldg(p); }
@@ -30,18 +34,21 @@ __device__ __forceinline__ float pt_load(const int16_t* p) {
   return __fmaf_rn(__int_as_float(0x4B400000 + (int)__ldg(p)), 1.0f / 32768.0f, -384.0f);
 }
 
+// grid (frame chunks, B): a CTA takes kPChunk consecutive frames of one segment (fine-grained CTAs keep the last
+// wave of a batch short: a whole 5 s segment per CTA left a third of the GPU idle at 1024 segments)
 template <class InT>
-__global__ void __launch_bounds__(kPWarps * 32) pitch_track_kernel(const InT* __restrict__ wav, int T, int nf, int n_out,
-                                                                   int32_t* __restrict__ lags_out, float* __restrict__ f0_out,
-                                                                   int32_t* __restrict__ voiced_out, int nv) {
+__global__ void __launch_bounds__(kPWarps * 32) pitch_lags_kernel(const InT* __restrict__ wav, int T, int nf,
+                                                                  int32_t* __restrict__ lags_out) {
   __shared__ float rows[kPWarps][kPRow];
-  __shared__ double red[kPWarps];
+  __shared__ double psum[kPWarps][kPRow + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const InT* x = wav + (size_t)blockIdx.x * T;
-  int32_t* lags = lags_out + (size_t)blockIdx.x * nf;
+  double* P = psum[warp];
+  const InT* x = wav + (size_t)blockIdx.y * T;
+  int32_t* lags = lags_out + (size_t)blockIdx.y * nf;
   float* s = rows[warp];
+  const int f_end = min(nf, (int)(blockIdx.x + 1) * kPChunk);
 
-  for (int f = warp; f < nf; f += kPWarps) {
+  for (int f = blockIdx.x * kPChunk + warp; f < f_end; f += kPWarps) {
     const int base = f * kPFrame;
 #pragma unroll
     for (int k = 0; k < kPRow / 32; ++k) {
@@ -49,32 +56,59 @@ __global__ void __launch_bounds__(kPWarps * 32) pitch_track_kernel(const InT* __
       s[lane + 32 * k] = (t < T) ? pt_load(x + t) : 0.0f;          // torch pads the waveform with zeros
     }
     __syncwarp();
-    float e1 = 0.0f;
+    // energies of the frame and of every shifted frame from ONE fp64 prefix sum of the squares (lane l scans the
+    // 13 consecutive samples 13 l .. 13 l + 12, a shuffle scan adds the lane offsets): e2[lag] = P[lag + 160] - P[lag]
+    // is exact to fp64, which halves the FMAs of the correlation loop below
+    {
+      double run[kPRow / 32];
+      double tot = 0.0;
 #pragma unroll
-    for (int k = 0; k < kPFrame / 32; ++k) { const float v = s[lane + 32 * k]; e1 = fmaf(v, v, e1); }
+      for (int k = 0; k < kPRow / 32; ++k) { const double v = (double)s[(kPRow / 32) * lane + k]; tot = fma(v, v, tot); run[k] = tot; }
+      double off = tot;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) e1 += __shfl_xor_sync(0xffffffffu, e1, o);
-    float c[6], e2[6];
+      for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
+      off -= tot;                                                  // exclusive offset of this lane
 #pragma unroll
-    for (int q = 0; q < 6; ++q) c[q] = e2[q] = 0.0f;
-    const float* sl = s + 1 + lane;                                // lag of slot q: 1 + lane + 32 q
-#pragma unroll 4
-    for (int i = 0; i < kPFrame; ++i) {
-      const float a = s[i];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float b = sl[i + 32 * q];
-        c[q] = fmaf(a, b, c[q]);
-        e2[q] = fmaf(b, b, e2[q]);
-      }
+      for (int k = 0; k < kPRow / 32; ++k) P[(kPRow / 32) * lane + k + 1] = off + run[k];
+      if (lane == 0) P[0] = 0.0;
     }
+    __syncwarp();
+    const float e1 = (float)(P[kPFrame] - P[0]);
+    // lane l owns the 7 consecutive lags 1 + 7 l .. 7 + 7 l (27 lanes cover 189 lags).  With consecutive lags the
+    // shifted samples slide through a 7-register window: a step costs one broadcast load of s[i], ONE new
+    // conflict-free load (stride 7 across lanes) and 7 FMAs, instead of one load per multiply-add.
+    float c[kPLpl], e2[kPLpl], b[kPLpl];
+    const float* sl = s + 1 + kPLpl * lane;                        // sl[i + q] = s[i + lag_q]
+#pragma unroll
+    for (int q = 0; q < kPLpl; ++q) {
+      c[q] = 0.0f;
+      b[q] = sl[q];
+      e2[q] = (float)(P[1 + kPLpl * lane + q + kPFrame] - P[1 + kPLpl * lane + q]);
+    }
+    auto steps = [&](int i0, auto nsteps) {
+      constexpr int NS = decltype(nsteps)::value;
+#pragma unroll
+      for (int u = 0; u < NS; ++u) {
+        const float a = s[i0 + u];
+        const float nb = sl[i0 + u + kPLpl];                       // the sample the window gains at the next step
+#pragma unroll
+        for (int q = 0; q < kPLpl; ++q) {
+          const float bv = b[(u + q) % kPLpl];                     // slot of lag q at step u of a block (static index)
+          c[q] = fmaf(a, bv, c[q]);
+        }
+        b[u % kPLpl] = nb;                                         // the slot lag 0 leaves becomes lag 6 of the next step
+      }
+    };
+#pragma unroll 1
+    for (int i0 = 0; i0 + kPLpl <= kPFrame; i0 += kPLpl) steps(i0, std::integral_constant<int, kPLpl>{});
+    steps((kPFrame / kPLpl) * kPLpl, std::integral_constant<int, kPFrame % kPLpl>{});
     __syncwarp();                                                  // the row is free for the next frame
     const float n1 = (1e-9f + sqrtf(e1)) * (1e-9f + sqrtf(e1));
     float bv = -3.4e38f, hv = -3.4e38f;
     int bl = 0x7fffffff, hl = 0x7fffffff;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const int lag = 1 + lane + 32 * q;
+    for (int q = 0; q < kPLpl; ++q) {
+      const int lag = 1 + kPLpl * lane + q;
       const float n2 = (1e-9f + sqrtf(e2[q])) * (1e-9f + sqrtf(e2[q]));
       const float v = c[q] / n1 / n2;
       if (lag > kPLagMin && lag <= kPLags) {
@@ -93,7 +127,17 @@ __global__ void __launch_bounds__(kPWarps * 32) pitch_track_kernel(const InT* __
     }
     if (lane == 0) lags[f] = (hv > 0.99f * bv) ? hl : bl;          // _combine_max(half, best, thresh = 0.99)
   }
-  __syncthreads();
+}
+
+// grid B: smoothing of the lag track and the voicing flags of one segment
+template <class InT>
+__global__ void __launch_bounds__(kPWarps * 32) pitch_finish_kernel(const InT* __restrict__ wav, int T, int nf, int n_out,
+                                                                    const int32_t* __restrict__ lags_in, float* __restrict__ f0_out,
+                                                                    int32_t* __restrict__ voiced_out, int nv) {
+  __shared__ double red[kPWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const InT* x = wav + (size_t)blockIdx.x * T;
+  const int32_t* lags = lags_in + (size_t)blockIdx.x * nf;
 
   // lower median over windows of 30 frames, 14 copies of the first value in front (_median_smoothing)
   float* f0 = f0_out + (size_t)blockIdx.x * n_out;
@@ -164,8 +208,9 @@ static int launch_pitch(const InT* wav, int B, int T, int32_t* lags, float* f0, 
   const int n_out = nf - (kPMedWin - 1 - (kPMedWin - 1) / 2) > 0 ? nf - (kPMedWin - 1 - (kPMedWin - 1) / 2) : 0;
   if (n_out > 0 && !f0) return MSA_ERR_BAD_ARGUMENT;           // fewer than 16 frames: no smoothed output (torchaudio raises)
   const int nv = (T >= kVWin) ? (T - kVWin) / kVHop + 1 : 0;
-  pitch_track_kernel<InT><<<B, kPWarps * 32, 0, st>>>(wav, T, nf, n_out, lags, f0, voiced, nv);
-  note_launches(1);
+  pitch_lags_kernel<InT><<<dim3((nf + kPChunk - 1) / kPChunk, B), kPWarps * 32, 0, st>>>(wav, T, nf, lags);
+  pitch_finish_kernel<InT><<<B, kPWarps * 32, 0, st>>>(wav, T, nf, n_out, lags, f0, voiced, nv);
+  note_launches(2);
   return (int)cudaGetLastError();
 }
 
