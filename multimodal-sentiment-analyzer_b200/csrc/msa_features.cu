@@ -88,8 +88,9 @@ int features_smem_bytes(int T, int c) {
 template <class InT>
 static int launch_features(const InT* wav, int B, int T, const float* emo8, float* feat31, float* detail,
                            float* dbg_mfcc, int flags, int parts, int cluster_size, cudaStream_t stream) {
-  if (!wav || !feat31 || B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
-  if (B == 0) return MSA_OK;
+  if (B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
+  if (B == 0) return MSA_OK;                                   // an empty batch has no buffers to check
+  if (!wav || !feat31) return MSA_ERR_BAD_ARGUMENT;
   int c = cluster_size ? cluster_size : auto_cluster_size(B, T);
   if (c != 1 && c != 2 && c != 4 && c != 8) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
   // torch.stft's reflect padding needs T > n_fft/2: below that the reference's method raises and

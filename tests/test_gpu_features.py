@@ -179,3 +179,33 @@ def test_full_size_batch_properties(ana):
         x = synth.pcm_to_f32(pcm[i].cpu().numpy())
         close(d[i, 10:23], fx.timbre(x), what="timbre")
         close(d[i, 27:31], fx.quality4(x), what="quality")
+
+
+@pytest.mark.parametrize("T", [1, 79, 80, 150, 200, 201, 256, 257, 300, 399, 400, 401, 513, 1599, 1600])
+def test_tiny_lengths_match_oracle(ana, T):
+    """Segments shorter than a transform's padding make the reference's method raise and return its default
+    (zeros); the thresholds differ per feature (timbre needs T > 200, "pitch" T > 256, rhythm T >= 400, consistency
+    a full 1600-sample block).  The oracle reproduces the reference on every one of these lengths."""
+    x = synth.pcm_to_f32(synth.segment_pcm(50 + T, T))
+    _, det, _ = _detail(ana, x[None])
+    d = det[0]
+    raw, q = fx.raw_features(x), fx.quality4(x)
+    assert abs(d[8]) <= 1e-6 and np.isnan(d[9])
+    close(d[10:23], raw[10:23], what="timbre")
+    assert d[23] == raw[23]
+    close(d[24:26], raw[24:26], what="rhythm")
+    assert np.float32(d[26]) == np.float32(raw[26])
+    close(d[27:31], q, what="quality")
+    assert d[72] == (T if T > 256 else 0)                            # residual samples: all of them, or the part is off
+
+
+def test_empty_batch_and_bad_arguments(ana):
+    from msa_b200 import _lib
+    lib = ana._lib
+    feat = torch.zeros(1, 31, device=ana.device)
+    w = torch.zeros(1, 80000, device=ana.device)
+    assert lib.msa_features_f32(_lib.ptr(w), 0, 80000, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == 0     # B = 0: nothing to do
+    assert lib.msa_features_f32(None, 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == -1
+    assert lib.msa_features_f32(_lib.ptr(w), 1, 0, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == -1
+    assert lib.msa_features_f32(_lib.ptr(w), 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 3, None) == -1    # cluster size must be 1/2/4/8
+    assert ana.analyze_batch(torch.zeros(0, 80000, device=ana.device)).shape == (0, 31)
