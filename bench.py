@@ -165,6 +165,8 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ GPU arm
 def run_native(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps "NCCL version ..." off stdout: one JSON line only
+        os.environ["NCCL_DEBUG"] = "WARN"
     import numpy as np
     import torch
     import torch.distributed as dist

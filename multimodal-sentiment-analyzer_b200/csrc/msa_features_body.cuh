@@ -505,6 +505,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
       float pw[S][28];
       float share[S][52];
+      float cdelta[S][4][4];                                       // [frame][slot] clamp deltas of the current quad
+      float asum[S][2];
       float* fbuf = reinterpret_cast<float*>(wbuf);
       // a contiguous run of quads per warp (adjacent quads share a hop of samples in L1)
       const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
@@ -602,7 +604,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         env.wsync();
         // mel energies of the lane's 4 filters for the 4 frames, dB, DCT shares
         env.lanes([&](int lane, int li) {
-          float db[4][4];                                            // [frame][slot]
+          float db[4][4];                                            // [frame][slot], never clamped: the DCT of the clamp
+          float (&cl)[4][4] = cdelta[li];                            // deltas (thr - dB where dB < thr) is added separately
           static_for<0, 4>([&](auto sc) {
             constexpr int s = decltype(sc)::value;
             constexpr int trips = (s == 0) ? kMelTrip0 : (s == 1) ? kMelTrip1 : (s == 2) ? kMelTrip2 : kMelTrip3;
@@ -627,8 +630,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               if (live) {
                 dmax[li] = fmaxf(dmax[li], d);
                 dmin[li] = fminf(dmin[li], d);
-                d = fmaxf(d, thr);
               }
+              cl[j][s] = (live && d < thr) ? thr - d : 0.0f;         // thr = -inf in pass 0
               db[j][s] = d;
             }
           });
@@ -654,17 +657,64 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         });
         env.wsync();
         env.lanes([&](int lane, int li) {
-          (void)li;
   #pragma unroll
           for (int half = 0; half < 2; ++half) {
             const int v = lane + 32 * half;
+            float a = 0.0f;
             if (v < 52) {
-              float a = 0.0f;
   #pragma unroll
               for (int j = 0; j < 32; ++j) a += fbuf[v * 33 + j];
-              const int fr = m0 + v / kMfcc;
-              if (fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = a;
             }
+            asum[li][half] = a;
+          }
+        });
+        env.wsync();
+        if (pass == 1) {
+          // clamped pass: the DCT of the clamp deltas, accumulated per lane in slot order and summed over the
+          // lanes in lane order - the very arithmetic clamp_fix() applies to a candidate list, so both paths
+          // (and therefore every way of splitting a batch over clusters) give the same bits
+          env.lanes([&](int lane, int li) {
+            const float (&cl)[4][4] = cdelta[li];
+  #pragma unroll
+            for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
+            const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
+            static_for<0, kDctQuads>([&](auto ic) {
+              constexpr int i = decltype(ic)::value;
+              const float4 q = dq[i * 32 + lane];
+              const float qc[4] = {q.x, q.y, q.z, q.w};
+              static_for<0, 4>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
+  #pragma unroll
+                for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(cl[j][s], qc[c], share[li][j * kMfcc + k]);
+              });
+            });
+          });
+          env.lanes([&](int lane, int li) {
+  #pragma unroll
+            for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
+          });
+          env.wsync();
+          env.lanes([&](int lane, int li) {
+  #pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int v = lane + 32 * half;
+              if (v < 52) {
+                float ca = 0.0f;
+  #pragma unroll
+                for (int j = 0; j < 32; ++j) ca += fbuf[v * 33 + j];
+                asum[li][half] += ca;
+              }
+            }
+          });
+          env.wsync();
+        }
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int v = lane + 32 * half;
+            const int fr = m0 + v / kMfcc;
+            if (v < 52 && fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = asum[li][half];
           }
         });
         env.wsync();
@@ -691,21 +741,54 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     if (!slow) break;
   }
   if (fix && !slow) {
-    env.lanes([&](int lane, int li) {
-      (void)li;
-      if (lane < kMfcc) {
-        for (int e = 0; e < ncand; ++e) {
-          const int2 ce = clist[e];
-          const float d = int_as_float(ce.y);
-          if (d < thr) {
-            const int m = ce.x & 127, q = (m >> 5) * kMfcc + lane;
-            const float w = tb->dctq[((q >> 2) * 32 + (m & 31)) * 4 + (q & 3)];
-            float* o = mfl + (ce.x >> 7) * kMfcc + lane;
-            *o = fmaf(w, thr - d, *o);
+    // clamp_fix: per quad with clamped candidates, scatter delta * dct into the [frame x coefficient][lane] tile
+    // (entries of one (frame, lane) arrive in slot order), sum the tile over the lanes in lane order and add the
+    // result to the quad's rows: bit for bit what the clamped pass computes
+    float* fb = reinterpret_cast<float*>(wbuf);
+    int e0 = 0;
+    while (e0 < ncand) {                                   // ncand and the list are warp-uniform
+      const int quad = (clist[e0].x >> 7) >> 2;
+      int e1 = e0;
+      bool any = false;
+      while (e1 < ncand && ((clist[e1].x >> 7) >> 2) == quad) { any = any || (int_as_float(clist[e1].y) < thr); ++e1; }
+      if (any) {
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          for (int v = 0; v < 52; ++v) fb[v * 33 + lane] = 0.0f;
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          if (lane < kMfcc) {
+            for (int e = e0; e < e1; ++e) {
+              const int2 ce = clist[e];
+              const float d = int_as_float(ce.y);
+              if (d < thr) {
+                const int m = ce.x & 127, j = (ce.x >> 7) & 3, q = (m >> 5) * kMfcc + lane;
+                const float w = tb->dctq[((q >> 2) * 32 + (m & 31)) * 4 + (q & 3)];
+                float* o = fb + (j * kMfcc + lane) * 33 + (m & 31);
+                *o = fmaf(thr - d, w, *o);
+              }
+            }
           }
-        }
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          for (int half = 0; half < 2; ++half) {
+            const int v = lane + 32 * half;
+            const int fl = 4 * quad + v / kMfcc;
+            if (v < 52 && fl < nfr) {
+              float ca = 0.0f;
+              for (int j = 0; j < 32; ++j) ca += fb[v * 33 + j];
+              mfl[fl * kMfcc + v % kMfcc] += ca;
+            }
+          }
+        });
+        env.wsync();
       }
-    });
+      e0 = e1;
+    }
   }
   env.sync();
 

@@ -209,3 +209,27 @@ def test_empty_batch_and_bad_arguments(ana):
     assert lib.msa_features_f32(_lib.ptr(w), 1, 0, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == -1
     assert lib.msa_features_f32(_lib.ptr(w), 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 3, None) == -1    # cluster size must be 1/2/4/8
     assert ana.analyze_batch(torch.zeros(0, 80000, device=ana.device)).shape == (0, 31)
+
+
+def test_results_do_not_depend_on_cluster_size(ana):
+    """One segment per CTA, or split over 2 / 4 / 8 CTAs (what small batches and streaming use): the same bits,
+    whichever top_db path (patch list / clamped pass) each CTA takes.  Column 8 ("pitch") is the rounding residue of
+    the STFT -> ISTFT round trip and depends on the summation tree (|v| <= 1e-6 either way)."""
+    rng = np.random.default_rng(5)
+    t = np.arange(80000) / 16000.0
+    flip = 0.3 * np.sin(2 * np.pi * 180 * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.004 * rng.standard_normal(80000)
+    flip = np.round(np.clip(flip, -1, 1) * 32767).astype(np.int16).astype(np.float32) / np.float32(32768)
+    adv = synth.adversarial_cases()
+    x = np.stack([synth.pcm_to_f32(synth.segment_pcm(1234)), flip, adv["tone_220"], adv["half_silence"], adv["white_0p1"]])
+    cols = [c for c in range(63) if c != 8]
+    ref = None
+    for c in (1, 2, 4, 8):
+        feat, det, mf = _detail(ana, x, cluster=c)
+        if ref is None:
+            ref = (feat, det, mf)
+            continue
+        assert np.array_equal(feat, ref[0]), c
+        bad = [k for k in cols if not np.array_equal(det[:, k], ref[1][:, k], equal_nan=True)]
+        assert not bad, (c, bad)
+        assert np.array_equal(mf, ref[2]), c
+        assert np.all(np.abs(det[:, 8]) <= 1e-6)
