@@ -279,13 +279,15 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int per = ceil_div(2 * nn, NR);
       const int i0 = (r * per < 2 * nn) ? r * per : 2 * nn;
       const int i1 = (i0 + per < 2 * nn) ? i0 + per : 2 * nn;
+      // exact squares summed in fp64: which lane visits which sample depends on the cluster size and the CTA shape,
+      // and the result must not (a float running sum per lane would differ in its last bits)
       env.lanes([&](int lane, int li) {
-        float acc = 0.0f;
+        double acc = 0.0;
         for (int i = i0 + env.warp * 32 + lane; i < i1; i += env.nthreads) {
-          const float v = env.ld(x + ((i < nn) ? i : T - 2 * nn + i));
-          acc = fmaf(v, v, acc);
+          const double v = (double)env.ld(x + ((i < nn) ? i : T - 2 * nn + i));
+          acc += v * v;
         }
-        e_noi[li] = (double)acc;
+        e_noi[li] = acc;
       });
     }
     const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};

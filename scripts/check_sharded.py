@@ -23,7 +23,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
-S, T, N_SPK = 720, 80000, 4
+S, T, N_SPK = int(os.environ.get("MSA_CHECK_SEGMENTS", "720")), 80000, 4   # 720 x 5 s = one hour
 hour = synth.fast_segments_pcm(11, S).reshape(-1)                    # 57.6 M samples, identical on every rank (seeded)
 face, text = synth.face_rows(12, S), synth.text_rows(13, S)
 speaker = np.random.default_rng(14).integers(0, N_SPK, S).astype(np.int32)

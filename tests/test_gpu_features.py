@@ -233,3 +233,17 @@ def test_results_do_not_depend_on_cluster_size(ana):
         assert not bad, (c, bad)
         assert np.array_equal(mf, ref[2]), c
         assert np.all(np.abs(det[:, 8]) <= 1e-6)
+
+
+def test_batch_of_512_is_cluster_size_invariant(ana):
+    """The sharded hour of BASELINE configs[2] runs 90 segments per GPU on 8 GPUs (2 CTAs per segment) and 720 on one
+    (1 CTA per segment): every bit of the result table must agree, including the quality floats whose sums are
+    partitioned differently."""
+    pcm = synth.fast_segments_pcm(11, 512)
+    f1, d1, _ = _detail(ana, pcm, cluster=1)
+    f2, d2, _ = _detail(ana, pcm, cluster=2)
+    assert np.array_equal(f1, f2)
+    cols = [c for c in range(63) if c != 8]
+    bad = [k for k in cols if not np.array_equal(d1[:, k], d2[:, k], equal_nan=True)]
+    assert not bad, bad
+    assert (f1[:, 28] > 0).any()                                    # some segments have a non-zero SNR term
