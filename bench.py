@@ -63,6 +63,16 @@ def measured_peaks():
     return 6650.0, "fallback"
 
 
+def measured_tensor_peak():
+    """Sustained dense bf16 TFLOP/s (the fusion chain is timed inside a long step)."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured"
+    return 1590.0, "fallback"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -340,6 +350,11 @@ def run_native(args):
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SEGMENT * S, "peak_source": peak_src,
                          "ms_per_launch": ms_feat, "note": "bound by fp32 instruction issue (register FFTs: ~58 FLOP per waveform byte vs a ridge of ~11), not by HBM: ncu smsp__issue_active 57 %, see DESIGN.md 4.1"},
             "kernels_ms": {"features": ms_feat, "fusion_chain": ms_fus},
+            "fusion_tensor": (lambda pk: {"bound": "tensor", "achieved": 9069568.0 * S / (ms_fus / 1000.0) / 1e12, "peak": pk[0], "unit": "TFLOP/s",
+                                          "frac": 9069568.0 * S / (ms_fus / 1000.0) / 1e12 / pk[0], "peak_source": pk[1],
+                                          "note": "algorithmic FLOP (9,069,568 per row, counted once; three bf16 MMAs are issued per product). "
+                                                  "At this batch the 5-launch chain is latency-bound; batch 65536 reaches 248 TFLOP/s "
+                                                  "(profiles/r1_v5_fusion_only_times.jsonl)"})(measured_tensor_peak()),
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(pcm_host.numel() * 2 + face_host.numel() * 4 + text_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(rows_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps, "input": "int16 PCM from pinned host memory", "h2d_only_ms": ms_h2d,
