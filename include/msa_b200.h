@@ -72,6 +72,17 @@ int msa_features_smem_bytes(int T, int cluster_size);
 int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
                      float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream);
 
+/* Optional scratch table for msa_features_ws_*: when a segment holds long stretches far below its loudest mel
+ * value (pauses, digital silence), the top_db = 80 clamp touches more values than the kernel's on-chip candidate
+ * lists hold; with a workspace of msa_features_workspace_bytes(B, T) bytes (device memory, contents irrelevant)
+ * those quads save their mel dB values there and the clamp is applied without a second FFT.  Without it (or with
+ * the plain msa_features_* calls) the affected quads are recomputed: the results are bit-identical either way. */
+size_t msa_features_workspace_bytes(int B, int T);
+int msa_features_ws_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail, float* dbg_mfcc,
+                        int flags, int parts, int cluster_size, void* workspace, size_t workspace_bytes, void* stream);
+int msa_features_ws_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail, float* dbg_mfcc,
+                        int flags, int parts, int cluster_size, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same, from int16 PCM (pcm_s16le as written by offline_processor.py:87-91 and
  * streaming_processor.py:185-196); samples are scaled by 1/32768 like torchaudio.load. */
 int msa_features_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail,

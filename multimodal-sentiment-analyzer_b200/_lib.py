@@ -22,6 +22,9 @@ _SIGNATURES = {
     "msa_features_smem_bytes": (c_int, [c_int, c_int]),
     "msa_features_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "msa_features_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "msa_features_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "msa_features_ws_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "msa_features_ws_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "msa_fusion_packed_bytes": (c_size_t, []),
     "msa_fusion_workspace_bytes": (c_size_t, [c_int]),
     "msa_fusion_num_tensors": (c_int, []),

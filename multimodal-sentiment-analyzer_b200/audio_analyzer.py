@@ -47,6 +47,7 @@ class AudioAnalyzer:
         self.strict_reference = strict_reference
         self.emotion_embedding: Optional[torch.Tensor] = None   # injected [1, 8] output of the out-of-scope SER model
         self._lib = _lib.lib()
+        self._ws: Optional[torch.Tensor] = None
         logger.info("AudioAnalyzer (msa_b200, sm_100a) on %s, sample_rate %d", self.device, sample_rate)
 
     # ------------------------------------------------------------------ kernel entry
@@ -60,11 +61,19 @@ class AudioAnalyzer:
         feat = torch.empty(B, 31, device=self.device, dtype=torch.float32)
         detail = torch.empty(B, _lib.DETAIL_STRIDE, device=self.device, dtype=torch.float32)
         mfcc = torch.empty(B, T // 200 + 1, 13, device=self.device, dtype=torch.float32) if want_mfcc else None
-        fn = self._lib.msa_features_s16 if waves.dtype == torch.int16 else self._lib.msa_features_f32
+        fn = self._lib.msa_features_ws_s16 if waves.dtype == torch.int16 else self._lib.msa_features_ws_f32
+        ws = self._workspace(B, T)
         rc = fn(_lib.ptr(waves), B, T, _lib.ptr(emo8), _lib.ptr(feat), _lib.ptr(detail), _lib.ptr(mfcc), self._flags(), parts, 0,
-                _lib.current_stream_ptr(self.device))
+                _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
         _lib.check(rc, "msa_features")
         return feat, detail, mfcc
+
+    def _workspace(self, B: int, T: int) -> torch.Tensor:
+        """Grow-only scratch table for the top_db clamp of pause-heavy segments (msa_features_workspace_bytes)."""
+        need = self._lib.msa_features_workspace_bytes(B, T)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(int(need), 1), dtype=torch.uint8, device=self.device)
+        return self._ws
 
     def _mono(self, waveform: torch.Tensor) -> torch.Tensor:
         """The reference's only working layout is [1, T]."""
@@ -105,9 +114,10 @@ class AudioAnalyzer:
         if (not waveforms.is_contiguous() or not out_rows.is_contiguous() or out_rows.shape != (B, 31)
                 or out_rows.dtype != torch.float32 or waveforms.dtype not in (torch.int16, torch.float32)):
             raise ValueError("analyze_into needs contiguous [B, T] int16/fp32 waves and a contiguous fp32 [B, 31] output")
-        fn = self._lib.msa_features_s16 if waveforms.dtype == torch.int16 else self._lib.msa_features_f32
+        fn = self._lib.msa_features_ws_s16 if waveforms.dtype == torch.int16 else self._lib.msa_features_ws_f32
+        ws = self._workspace(B, T)
         rc = fn(_lib.ptr(waveforms), B, T, _lib.ptr(self._emo(B, emotion_probs)), _lib.ptr(out_rows), None, None, self._flags(),
-                _lib.PART_ALL, 0, _lib.current_stream_ptr(self.device))
+                _lib.PART_ALL, 0, _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
         _lib.check(rc, "msa_features")
 
     def track_pitch(self, waveforms: torch.Tensor, with_voicing: bool = True):

@@ -61,6 +61,8 @@ int feat_threads() {
 // Smallest cluster whose per-CTA shared-memory layout lets two CTAs share an SM, else the smallest that
 // fits at all (the per-segment MFCC tile and the energy atoms are split over the ranks; everything else
 // is per warp).
+size_t features_workspace_bytes(int B, int T);
+
 int features_cluster_size(int T) {
   if (T < 1) return 0;
   const int nwarps = feat_threads() / 32;
@@ -80,6 +82,12 @@ static int auto_cluster_size(int B, int T) {
   return c;
 }
 
+size_t features_workspace_bytes(int B, int T) {
+  if (B < 1 || T < 1) return 0;
+  const size_t quads = (size_t)((T / kHopM + 1) + 3) / 4;
+  return (size_t)B * quads * 16 * 32 * sizeof(float);
+}
+
 int features_smem_bytes(int T, int c) {
   if (T < 1 || c < 1) return 0;
   return feat_layout(T, c, feat_threads() / 32).total;
@@ -87,7 +95,8 @@ int features_smem_bytes(int T, int c) {
 
 template <class InT>
 static int launch_features(const InT* wav, int B, int T, const float* emo8, float* feat31, float* detail,
-                           float* dbg_mfcc, int flags, int parts, int cluster_size, cudaStream_t stream) {
+                           float* dbg_mfcc, int flags, int parts, int cluster_size, void* workspace, size_t ws_bytes,
+                           cudaStream_t stream) {
   if (B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
   if (B == 0) return MSA_OK;                                   // an empty batch has no buffers to check
   if (!wav || !feat31) return MSA_ERR_BAD_ARGUMENT;
@@ -111,6 +120,8 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.feat31 = feat31;
   P.detail = detail;
   P.dbg_mfcc = dbg_mfcc;
+  // optional scratch table of mel dB values (see FeatParams::dbscratch); too small or absent: quads are recomputed
+  P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
   P.flags = flags;
   P.parts = parts;
@@ -144,16 +155,34 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
 extern "C" int msa_features_cluster_size(int T) { return msa::features_cluster_size(T); }
 extern "C" int msa_features_smem_bytes(int T, int c) { return msa::features_smem_bytes(T, c); }
 
+extern "C" size_t msa_features_workspace_bytes(int B, int T) { return msa::features_workspace_bytes(B, T); }
+
 extern "C" int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
                                 float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream) {
   msa::reset_launches();
-  return msa::launch_features<float>(wav, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size,
+  return msa::launch_features<float>(wav, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size, nullptr, 0,
                                      (cudaStream_t)stream);
+}
+
+extern "C" int msa_features_ws_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
+                                   float* dbg_mfcc, int flags, int parts, int cluster_size, void* workspace, size_t ws_bytes,
+                                   void* stream) {
+  msa::reset_launches();
+  return msa::launch_features<float>(wav, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size, workspace, ws_bytes,
+                                     (cudaStream_t)stream);
+}
+
+extern "C" int msa_features_ws_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail,
+                                   float* dbg_mfcc, int flags, int parts, int cluster_size, void* workspace, size_t ws_bytes,
+                                   void* stream) {
+  msa::reset_launches();
+  return msa::launch_features<int16_t>(pcm, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size, workspace, ws_bytes,
+                                       (cudaStream_t)stream);
 }
 
 extern "C" int msa_features_s16(const int16_t* pcm, int B, int T, const float* emo8, float* feat31, float* detail,
                                 float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream) {
   msa::reset_launches();
-  return msa::launch_features<int16_t>(pcm, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size,
+  return msa::launch_features<int16_t>(pcm, B, T, emo8, feat31, detail, dbg_mfcc, flags, parts, cluster_size, nullptr, 0,
                                        (cudaStream_t)stream);
 }

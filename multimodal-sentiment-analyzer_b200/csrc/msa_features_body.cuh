@@ -71,6 +71,8 @@ struct FeatParams {
   float* feat31;         // [B, 31]  LN31[:27] ++ quality4, nan_to_num'd (fusion input row)
   float* detail;         // [B, 96]  or null: raw27, quality4, ln31, diagnostics
   float* dbg_mfcc;       // [B, nFm, 13] or null
+  float* dbscratch;      // [B, ceil(nFm / 4), 16, 32] or null: mel dB values of the quads whose top_db candidates did not fit
+                         // their warp's list, so that applying the clamp later needs no second FFT
   const FeatureTables* tab;
   int flags;
   int parts;
@@ -500,24 +502,91 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   }
   float thr = -3.0e38f, gmax = -3.0e38f, gmin = 3.0e38f;
   int ncand = 0;                                           // warp-uniform length of this warp's candidate list
-  bool fix = false, slow = false;
+  int ovf_task = 0x7fffffff;                               // warp-uniform: first task (quad) whose candidates did not fit
+  bool fix = false, slow = false, slow_w = false;          // slow: some warp of this CTA overflowed; slow_w: this warp did
   for (int pass = 0; pass < 2; ++pass) {
     const float cand_p = (pass == 0) ? cand : -3.0e38f;
       float dmax[S], dmin[S];
       for (int i = 0; i < S; ++i) { dmax[i] = -3.0e38f; dmin[i] = 3.0e38f; }
       float pw[S][28];
       float share[S][52];
-      float cdelta[S][4][4];                                       // [frame][slot] clamp deltas of the current quad
-      float asum[S][2];
       float* fbuf = reinterpret_cast<float*>(wbuf);
+      float cdelta[S][4][4];                                       // [frame][slot] clamp deltas of the current quad
+      float dbs[S][4][4];                                          // [frame][slot] mel dB values of the current quad
+      float asum[S][2], casum[S][2];
+      // DCT of the clamp deltas in cdelta, summed over the lanes in lane order -> casum (v = lane + 32 half): the one
+      // arithmetic every way of applying the clamp uses (patch list, saved dB values, recomputed quad)
+      auto delta_dct = [&]() {
+        env.lanes([&](int lane, int li) {
+          const float (&cl)[4][4] = cdelta[li];
+  #pragma unroll
+          for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
+          const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
+          static_for<0, kDctQuads>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            const float4 q = dq[i * 32 + lane];
+            const float qc[4] = {q.x, q.y, q.z, q.w};
+            static_for<0, 4>([&](auto cc) {
+              constexpr int c = decltype(cc)::value;
+              constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(cl[j][s], qc[c], share[li][j * kMfcc + k]);
+            });
+          });
+        });
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
+        });
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+  #pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int v = lane + 32 * half;
+            float ca = 0.0f;
+            if (v < 52) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) ca += fbuf[v * 33 + j];
+            }
+            casum[li][half] = ca;
+          }
+        });
+        env.wsync();
+      };
       // a contiguous run of quads per warp (adjacent quads share a hop of samples in L1)
       const int ntasks = (nfr > 0) ? mq_end - mq_begin : 0;
       const int tper = ceil_div(ntasks, NW);
       const int t_lo = env.warp * tper;
       const int t_begin = (t_lo < ntasks) ? t_lo : ntasks;
       const int t_end = (t_begin + tper < ntasks) ? t_begin + tper : ntasks;
-      for (int task = t_begin; task < t_end; ++task) {
+      // pass 1: only the warps whose list overflowed, from the quad at which it did (earlier quads are patched from the list)
+      for (int task = (pass == 0) ? t_begin : (slow_w ? ovf_task : t_end); task < t_end; ++task) {
         const int m0 = 4 * (mq_begin + task);
+        if (pass == 1 && P.dbscratch != nullptr) {
+          // the quad's dB values were saved by pass 0: clamp deltas -> delta DCT -> add to the rows, no FFT
+          const float* sv = P.dbscratch + (((size_t)seg * nQm + (mq_begin + task)) * 16) * 32;
+          env.lanes([&](int lane, int li) {
+  #pragma unroll
+            for (int j = 0; j < 4; ++j)
+  #pragma unroll
+              for (int s = 0; s < 4; ++s) {
+                const float d = sv[(4 * j + s) * 32 + lane];
+                const bool live = tb->mel_dead[32 * s + lane] == 0 && (m0 + j) < nFm;
+                cdelta[li][j][s] = (live && d < thr) ? thr - d : 0.0f;
+              }
+          });
+          delta_dct();
+          env.lanes([&](int lane, int li) {
+  #pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int v = lane + 32 * half;
+              const int fr = m0 + v / kMfcc;
+              if (v < 52 && fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] += casum[li][half];
+            }
+          });
+          env.wsync();
+          continue;
+        }
         const int s0 = kHopM * m0 - kNfftM / 2;
         const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);
         for (int h = 0; h < 2; ++h) {
@@ -606,7 +675,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         env.wsync();
         // mel energies of the lane's 4 filters for the 4 frames, dB, DCT shares
         env.lanes([&](int lane, int li) {
-          float db[4][4];                                            // [frame][slot], never clamped: the DCT of the clamp
+          float (&db)[4][4] = dbs[li];                               // [frame][slot], never clamped: the DCT of the clamp
           float (&cl)[4][4] = cdelta[li];                            // deltas (thr - dB where dB < thr) is added separately
           static_for<0, 4>([&](auto sc) {
             constexpr int s = decltype(sc)::value;
@@ -653,6 +722,20 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           });
         });
         env.wsync();
+        if (pass == 0) {
+          // the list overflowed at this quad (or earlier): from here on the quads' dB values go to the scratch
+          // table instead, so pass 1 can apply the clamp without recomputing them
+          if (ncand > kClampCap && ovf_task > task) ovf_task = task;
+          if (ovf_task <= task && P.dbscratch != nullptr) {
+            float* sv = P.dbscratch + (((size_t)seg * nQm + (mq_begin + task)) * 16) * 32;
+            env.lanes([&](int lane, int li) {
+  #pragma unroll
+              for (int j = 0; j < 4; ++j)
+  #pragma unroll
+                for (int s = 0; s < 4; ++s) sv[(4 * j + s) * 32 + lane] = dbs[li][j][s];
+            });
+          }
+        }
         env.lanes([&](int lane, int li) {
   #pragma unroll
           for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
@@ -671,45 +754,13 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           }
         });
         env.wsync();
-        if (pass == 1) {
-          // clamped pass: the DCT of the clamp deltas, accumulated per lane in slot order and summed over the
-          // lanes in lane order - the very arithmetic clamp_fix() applies to a candidate list, so both paths
-          // (and therefore every way of splitting a batch over clusters) give the same bits
+        if (pass == 1) {                                             // recomputed quad (no scratch table): add the delta DCT
+          delta_dct();
           env.lanes([&](int lane, int li) {
-            const float (&cl)[4][4] = cdelta[li];
-  #pragma unroll
-            for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
-            const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
-            static_for<0, kDctQuads>([&](auto ic) {
-              constexpr int i = decltype(ic)::value;
-              const float4 q = dq[i * 32 + lane];
-              const float qc[4] = {q.x, q.y, q.z, q.w};
-              static_for<0, 4>([&](auto cc) {
-                constexpr int c = decltype(cc)::value;
-                constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
-  #pragma unroll
-                for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(cl[j][s], qc[c], share[li][j * kMfcc + k]);
-              });
-            });
+            (void)lane;
+            asum[li][0] += casum[li][0];
+            asum[li][1] += casum[li][1];
           });
-          env.lanes([&](int lane, int li) {
-  #pragma unroll
-            for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
-          });
-          env.wsync();
-          env.lanes([&](int lane, int li) {
-  #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const int v = lane + 32 * half;
-              if (v < 52) {
-                float ca = 0.0f;
-  #pragma unroll
-                for (int j = 0; j < 32; ++j) ca += fbuf[v * 33 + j];
-                asum[li][half] += ca;
-              }
-            }
-          });
-          env.wsync();
         }
         env.lanes([&](int lane, int li) {
   #pragma unroll
@@ -736,23 +787,28 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     // amplitude_to_DB(top_db = 80): clamp to (segment max - 80).  The DCT is linear, so a clamped value only
     // adds dct[m][k] * (thr - dB) to its frame: every warp patches the frames it produced from its own
     // candidate list (a frame belongs to exactly one warp; list order is program order: deterministic).
-    // A list that overflowed (long digital silence inside a loud segment) redoes this CTA's pass clamped.
     thr = gmax - 80.0f;
     fix = (P.parts & kPartMfcc) && (dbmin < thr);
+    // the two ways of applying the clamp give the same bits, so each WARP chooses: patch from its list, or, if the
+    // list overflowed, redo its own quads with the deltas computed inline (pass 1 runs if any warp needs it)
     slow = fix && ctr[2] != 0;
+    slow_w = fix && ncand > kClampCap;
     if (!slow) break;
   }
-  if (fix && !slow) {
+  if (fix) {                                               // quads before the overflow (all of them when the list sufficed)
+    const int ovf_quad = ovf_task;                         // task index = this rank's local quad index = list key >> 9
     // clamp_fix: per quad with clamped candidates, scatter delta * dct into the [frame x coefficient][lane] tile
     // (entries of one (frame, lane) arrive in slot order), sum the tile over the lanes in lane order and add the
     // result to the quad's rows: bit for bit what the clamped pass computes
     float* fb = reinterpret_cast<float*>(wbuf);
     int e0 = 0;
-    while (e0 < ncand) {                                   // ncand and the list are warp-uniform
+    const int n_list = (ncand < kClampCap) ? ncand : kClampCap;
+    while (e0 < n_list) {                                  // the list and its length are warp-uniform
       const int quad = (clist[e0].x >> 7) >> 2;
       int e1 = e0;
       bool any = false;
-      while (e1 < ncand && ((clist[e1].x >> 7) >> 2) == quad) { any = any || (int_as_float(clist[e1].y) < thr); ++e1; }
+      while (e1 < n_list && ((clist[e1].x >> 7) >> 2) == quad) { any = any || (int_as_float(clist[e1].y) < thr); ++e1; }
+      if (quad >= ovf_quad) break;                           // that quad and the later ones are handled by pass 1
       if (any) {
         env.lanes([&](int lane, int li) {
           (void)li;

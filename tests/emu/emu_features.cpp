@@ -69,8 +69,17 @@ struct CpuEnv {
 
 }  // namespace msa
 
+extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nranks, int nwarps, const float* emo8,
+                               float* feat31, float* detail, float* dbg_mfcc, int flags, int parts, float* dbscratch);
+
 extern "C" int emu_features(const void* wav, int is_s16, int B, int T, int nranks, int nwarps, const float* emo8,
                             float* feat31, float* detail, float* dbg_mfcc, int flags, int parts) {
+  return emu_features_ws(wav, is_s16, B, T, nranks, nwarps, emo8, feat31, detail, dbg_mfcc, flags, parts, nullptr);
+}
+
+// dbscratch: [B, ceil((T / 200 + 1) / 4), 16, 32] floats or null (see FeatParams)
+extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nranks, int nwarps, const float* emo8,
+                               float* feat31, float* detail, float* dbg_mfcc, int flags, int parts, float* dbscratch) {
   using namespace msa;
   static FeatureTables tab;
   static bool built = false;
@@ -82,7 +91,7 @@ extern "C" int emu_features(const void* wav, int is_s16, int B, int T, int nrank
   if (T <= kNfftM / 2) parts &= ~kPartMfcc;
   FeatParams P{};
   P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.noise_n = (int)(0.05 * (double)T);
-  P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.tab = &tab; P.flags = flags; P.parts = parts;
+  P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.dbscratch = dbscratch; P.tab = &tab; P.flags = flags; P.parts = parts;
   const FeatLayout lay = feat_layout(T, nranks, nwarps);
   for (int seg = 0; seg < B; ++seg) {
     CpuCluster cl(nranks * nwarps);

@@ -29,15 +29,17 @@ def emu():
     return ctypes.CDLL(LIB)
 
 
-def run(lib, x, nranks=4, nwarps=4, flags=1, parts=7, emo=None):
+def run(lib, x, nranks=4, nwarps=4, flags=1, parts=7, emo=None, scratch=False):
     x = np.ascontiguousarray(x)
     B, T = x.shape
     feat = np.zeros((B, 31), np.float32)
     det = np.zeros((B, 96), np.float32)
     dbg = np.zeros((B, T // 200 + 1, 13), np.float32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    rc = lib.emu_features(p(x), int(x.dtype == np.int16), B, T, nranks, nwarps,
-                          None if emo is None else p(np.ascontiguousarray(emo)), p(feat), p(det), p(dbg), flags, parts)
+    ws = np.full((B, (T // 200 + 1 + 3) // 4, 16, 32), np.nan, np.float32) if scratch else None      # poisoned dB scratch table
+    rc = lib.emu_features_ws(p(x), int(x.dtype == np.int16), B, T, nranks, nwarps,
+                             None if emo is None else p(np.ascontiguousarray(emo)), p(feat), p(det), p(dbg), flags, parts,
+                             None if ws is None else p(ws))
     assert rc == 0
     return feat, det, dbg
 
@@ -154,8 +156,8 @@ def test_results_do_not_depend_on_the_partition(emu, name):
         x = synth.pcm_to_f32(synth.segment_pcm(1234)) if name == "seg1234" else synth.adversarial_cases()[name]
     ref = None
     paths = set()
-    for nranks, nwarps in ((1, 8), (2, 8), (8, 8), (1, 2), (4, 3)):
-        feat, det, dbg = run(emu, x[None], nranks, nwarps)
+    for nranks, nwarps, scratch in ((1, 8, False), (2, 8, False), (8, 8, True), (1, 2, False), (4, 3, True), (1, 2, True), (1, 8, True)):
+        feat, det, dbg = run(emu, x[None], nranks, nwarps, scratch=scratch)
         paths.add((det[0, 78], det[0, 75]))
         cur = (feat.copy(), det[:, :63].copy(), dbg.copy())
         if ref is None:

@@ -247,3 +247,32 @@ def test_batch_of_512_is_cluster_size_invariant(ana):
     bad = [k for k in cols if not np.array_equal(d1[:, k], d2[:, k], equal_nan=True)]
     assert not bad, bad
     assert (f1[:, 28] > 0).any()                                    # some segments have a non-zero SNR term
+
+
+def test_workspace_path_equals_recompute_path(ana):
+    """Pause-heavy segments overflow the on-chip top_db candidate lists; with the scratch table the clamp is applied
+    from saved dB values, without it the quads are recomputed: bit-identical results, and equal to the oracle."""
+    from msa_b200 import _lib
+    pcm = synth.fast_segments_pcm(21, 6)
+    pcm[:, 8000:24000] = 0
+    pcm[:, 48000:64000] = 0
+    pcm[3, :] = synth.segment_pcm(1234)                               # one ordinary segment in the batch
+    x = synth.pcm_to_f32(pcm)
+    f0, d0, m0 = _detail(ana, x)                                        # plain entry point: no workspace
+    w = torch.from_numpy(x).to(ana.device)
+    B, T = w.shape
+    ws = torch.full((ana._lib.msa_features_workspace_bytes(B, T) // 4,), float("nan"), device=ana.device)
+    feat = torch.empty(B, 31, device=ana.device); det = torch.empty(B, 96, device=ana.device); mf = torch.empty(B, T // 200 + 1, 13, device=ana.device)
+    for cluster in (1, 2, 8):
+        rc = ana._lib.msa_features_ws_f32(_lib.ptr(w), B, T, None, _lib.ptr(feat), _lib.ptr(det), _lib.ptr(mf), 1, 7, cluster,
+                                          _lib.ptr(ws), ws.numel() * 4, _lib.current_stream_ptr(ana.device))
+        assert rc == 0
+        torch.cuda.synchronize()
+        cols = [c for c in range(63) if c != 8]
+        assert np.array_equal(feat.cpu().numpy(), f0)
+        assert np.array_equal(det.cpu().numpy()[:, cols], d0[:, cols], equal_nan=True)
+        assert np.array_equal(mf.cpu().numpy(), m0)
+    assert d0[0, 75] == 1.0 and d0[3, 75] == 0.0                       # the paused segments took the overflow path
+    for i in (0, 3):
+        close(d0[i, 10:23], fx.timbre(x[i]), what="timbre")
+        close(d0[i, 27:31], fx.quality4(x[i]), what="quality")
