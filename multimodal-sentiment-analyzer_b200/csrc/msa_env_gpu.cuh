@@ -54,6 +54,24 @@ struct GpuEnv {
     }
   }
 
+  // one 16-byte load: 4 fp32 samples or 8 int16 samples starting at idx (0 beyond the end of the segment)
+  __device__ __forceinline__ void ldv(const float* x, int idx, int T, float* v) { ld4(x, idx, T, v); }
+  __device__ __forceinline__ void ldv(const int16_t* x, int idx, int T, float* v) {
+    const int16_t* p = x + idx;
+    if (idx + 7 < T && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(p));
+      const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        v[2 * i] = s16_to_f32((int)(short)(w[i] & 0xffff));
+        v[2 * i + 1] = s16_to_f32(w[i] >> 16);
+      }
+    } else {
+      ld4(x, idx, T, v);
+      ld4(x, idx + 4, T, v + 4);
+    }
+  }
+
   // block-wide copy of a 16-byte aligned table into shared memory
   __device__ __forceinline__ void copy16(void* dst, const void* src, int bytes) {
     const int4* s = reinterpret_cast<const int4*>(src);

@@ -234,30 +234,38 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
       n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
       float* scr = reinterpret_cast<float*>(wbuf);
-      // kK1Groups groups (5 float4 per lane each) are in flight per step: this phase is pure load latency
+      // kK1Groups groups of 640 samples are in flight per warp and step: this phase is pure load latency
       for (int gp = g0 + kK1Groups * env.warp; gp < g1; gp += kK1Groups * NW) {
         const int ng = (g1 - gp < kK1Groups) ? g1 - gp : kK1Groups;
+        // every 4 consecutive samples form one partial sum (entry = sample offset / 4 of the kK1Groups * 640 samples of
+        // the step); an atom is 20 consecutive entries.  fp32 input: one 16-byte load per entry; int16 input: one
+        // 16-byte load per TWO entries, so the bytes in flight (what this phase lives on) stay the same.  Entries are
+        // formed and added identically for both input types (bit-identical results).
         env.lanes([&](int lane, int li) {
-          float v[kK1Groups][5][4];
+          constexpr int kPer = (sizeof(InT) == 2) ? 8 : 4;                       // samples per load
+          constexpr int kLoads = kK1Groups * kGroup / (32 * kPer);               // loads per lane and step
+          float v[kLoads][kPer];
+          const int first = gp * kGroup, limit = (gp + ng) * kGroup;             // samples of this step
 #pragma unroll
-          for (int u = 0; u < kK1Groups; ++u)
+          for (int k = 0; k < kLoads; ++k) {
+            const int off = 32 * kPer * k + kPer * lane;
+            if (first + off < limit) env.ldv(x, first + off, T, v[k]);
+            else {
 #pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              if (u < ng) env.ld4(x, (gp + u) * kGroup + 128 * j + 4 * lane, T, v[u][j]);
-              else v[u][j][0] = v[u][j][1] = v[u][j][2] = v[u][j][3] = 0.0f;
+              for (int i = 0; i < kPer; ++i) v[k][i] = 0.0f;
             }
-#pragma unroll
-          for (int u = 0; u < kK1Groups; ++u) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) {
-              const float* q = v[u][j];
-              const float s = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
-              scr[160 * u + 32 * j + lane] = s;
-              acc += s;
-            }
-            e_tot[li] += (double)acc;
           }
+          double tot = 0.0;
+#pragma unroll
+          for (int k = 0; k < kLoads; ++k)
+#pragma unroll
+            for (int h4 = 0; h4 < kPer / 4; ++h4) {
+              const float* q = v[k] + 4 * h4;
+              const float sq = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
+              scr[(32 * kPer * k + kPer * lane) / 4 + h4] = sq;
+              tot += (double)sq;
+            }
+          e_tot[li] += tot;
         });
         env.wsync();
         env.lanes([&](int lane, int li) {

@@ -52,6 +52,8 @@ struct CpuEnv {
   template <class InT> void ld4(const InT* x, int idx, int T, float* v) {
     for (int i = 0; i < 4; ++i) v[i] = (idx + i < T) ? ld(x + idx + i) : 0.0f;
   }
+  void ldv(const float* x, int idx, int T, float* v) { ld4(x, idx, T, v); }
+  void ldv(const int16_t* x, int idx, int T, float* v) { ld4(x, idx, T, v); ld4(x, idx + 4, T, v + 4); }
   void copy16(void* dst, const void* src, int bytes) {
     if (warp == 0) std::memcpy(dst, src, bytes);
   }
