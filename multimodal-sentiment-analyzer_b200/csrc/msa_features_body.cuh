@@ -351,41 +351,40 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         const int f0 = 4 * quad;
         const int s0 = kHopP * f0 - kNfftP / 2;                  // first sample of frame f0
         const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
-        // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples
-        for (int h = 0; h < 2; ++h) {
-          env.lanes([&](int lane, int li) {
-            (void)li;
-            const int sb = s0 + 2 * h * kHopP;
+        // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples.  The quad spans
+        // 7 hop-blocks = 28 samples per lane, loaded once and shared by both FFTs (frames overlap by 3/4)
+        env.lanes([&](int lane, int li) {
+          (void)li;
+          float raw[28];
+          if (interior) {
+#pragma unroll
+            for (int i = 0; i < 28; ++i) raw[i] = env.ld(x + s0 + 32 * i + lane);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 28; ++i) raw[i] = xr(s0 + 32 * i + lane);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) xs[32 * i + lane] = raw[i];
+          static_for<0, 2>([&](auto hc) {
+            constexpr int h = decltype(hc)::value;
             const bool oka = (f0 + 2 * h) < nFp, okb = (f0 + 2 * h + 1) < nFp;
-            float raw[20];
-            if (interior) {
-#pragma unroll
-              for (int i = 0; i < 20; ++i) raw[i] = env.ld(x + sb + 32 * i + lane);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 20; ++i) raw[i] = xr(sb + 32 * i + lane);
-            }
-            if (h == 0) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) xs[32 * i + lane] = raw[i];
-            }
             c32 z[16];
             if (interior) {                                        // an interior quad has four valid frames: no selects
 #pragma unroll
               for (int n1 = 0; n1 < 16; ++n1) {
                 const float w = tb->win512[32 * n1 + lane];
-                z[n1] = c32{w * raw[n1], w * raw[n1 + 4]};
+                z[n1] = c32{w * raw[8 * h + n1], w * raw[8 * h + n1 + 4]};
               }
             } else {
 #pragma unroll
               for (int n1 = 0; n1 < 16; ++n1) {
                 const float w = tb->win512[32 * n1 + lane];
-                z[n1] = c32{oka ? w * raw[n1] : 0.0f, okb ? w * raw[n1 + 4] : 0.0f};
+                z[n1] = c32{oka ? w * raw[8 * h + n1] : 0.0f, okb ? w * raw[8 * h + n1 + 4] : 0.0f};
               }
             }
             pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
           });
-        }
+        });
         env.wsync();
         // pass B forward = the STFT spectrum X[k1 + 16 k2] of this row; phase_vocoder(rate = 1.0)
         // returns its input, so the inverse radix-32 follows in the same registers
@@ -603,7 +602,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
             if (lane < 25) {
               const int sb = s0 + 2 * h * kHopM;
               const bool oka = (m0 + 2 * h) < nFm, okb = (m0 + 2 * h + 1) < nFm;
-              float raw[24];
+              float raw[24];                                       // (sharing the quad's 40 samples between the two FFTs costs more in registers than the 8 loads it saves)
               if (interior) {
   #pragma unroll
                 for (int i = 0; i < 24; ++i) raw[i] = env.ld(x + sb + 25 * i + lane);
