@@ -196,6 +196,9 @@ int fusion_forward_simt(const float* face, const float* audio, const float* text
 int fusion_forward_tc(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
                       const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
                       cudaStream_t s);   // msa_fusion_tc.cu
+int fusion_forward_rows(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
+                        const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
+                        cudaStream_t s);   // msa_fusion_rows.cu
 
 static int fusion_impl();
 
@@ -221,7 +224,7 @@ static int fusion_impl() {
 }  // namespace msa
 
 extern "C" int msa_fusion_set_impl(int impl) {
-  if (impl != 0 && impl != 1) return MSA_ERR_BAD_ARGUMENT;
+  if (impl < 0 || impl > 2) return MSA_ERR_BAD_ARGUMENT;
   msa::g_impl = impl;
   return MSA_OK;
 }
@@ -250,7 +253,11 @@ extern "C" int msa_fusion_forward(const float* face, const float* audio, const f
   if (workspace_bytes < wl.total) return MSA_ERR_WORKSPACE;
   const PackedHeader& h = host_header();
   // MSA_FUSION_IMPL=simt selects the fp32 CUDA-core bring-up kernels (on-device cross-check of the
-  // tensor-core path; same C ABI, same results to fp32 rounding).  Default: tcgen05.
+  // tensor-core path; same C ABI, same results to fp32 rounding).  Default: tcgen05, except that a handful
+  // of rows (the streaming path: one row per chunk) takes the matrix-vector kernels of msa_fusion_rows.cu.
+  if (fusion_impl() == 0 && B <= kFusionRowsMaxBatch)
+    return fusion_forward_rows(face, audio, text, B, static_cast<const unsigned char*>(packed), h,
+                               static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream);
   if (fusion_impl() == 1) {
     Blob blob{static_cast<const unsigned char*>(packed), h};
     return fusion_forward_simt(face, audio, text, B, blob, static_cast<unsigned char*>(workspace), wl, logits7, argmax,

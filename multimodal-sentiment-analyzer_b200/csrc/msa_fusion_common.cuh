@@ -14,6 +14,7 @@
 namespace msa {
 
 constexpr int kFaceDim = 27, kAudioDim = 31, kTextDim = 783, kHidden = 1024, kHalf = 512, kOut = 7;
+constexpr int kFusionRowsMaxBatch = 8;                     // batches up to this size run as matrix-vector products (msa_fusion_rows.cu)
 constexpr int kFaceK = 64, kAudioK = 64, kTextK = 832;     // K padded to a multiple of 64 (one 128-byte swizzle row of bf16)
 
 struct TensorInfo { const char* name; int rows; int cols; };   // cols == 0: vector of `rows`

@@ -6,9 +6,12 @@
 //     rolloff 0.99).  After reducing by the gcd the transform is a polyphase FIR: output sample
 //     f * nw + j = sum_k kern[j][k] * xpad[f * orig + k], xpad = x shifted by `width` with zeros outside,
 //     K = 2 width + orig taps.  One CTA stages the input span of a tile of frames in shared memory; every
-//     thread owns one phase j and four frames, so a tap costs one coalesced table load ([k][j] layout), four
-//     broadcast shared-memory loads and four FMAs.  (The 3 -> 1 case, 48 kHz, is bandwidth bound; the
-//     441 -> 160 case, 44.1 kHz, is a 475-tap GEMM-shaped filter and runs on the fp32 pipes here.)
+//     thread owns one phase j and four frames, so a tap costs one coalesced table load, four shared-memory
+//     loads and four FMAs.  The windowed sinc of phase j is non-zero only within lowpass_filter_width zero
+//     crossings of its centre (torchaudio clamps t to +-6, where the Hann window vanishes): of the 475 taps
+//     of the 441 -> 160 filter (44.1 kHz) at most 35 per phase are non-zero.  The table is therefore stored
+//     compactly as [tap - first[j]][j] and a thread runs over its phase's run only; skipped taps are exact
+//     zeros, so the sums are bit-identical to the dense filter.  Both cases are bandwidth bound.
 //
 //  2. Feature-row normalisation: Face/Text/AudioFeatureNormalizer.normalize of src/utils/normalization.py:19-98
 //     (zero-pad or truncate to the target width, LayerNorm with eps 1e-5 and biased variance) and the
@@ -32,7 +35,9 @@ constexpr int kFrameTile = 4;                  // frames per thread
 
 struct ResampleTable {
   int dev, orig, nw, width, K;
-  float* kt;                                   // [K][nw] on the device
+  int run;                                     // longest run of non-zero taps of a phase
+  float* kt;                                   // [run][nw] on the device: kt[i][j] = kernel[j][first[j] + i]
+  int* first;                                  // [nw] first tap of phase j's run (first[j] + run <= K)
 };
 static std::mutex g_rs_mutex;
 static std::vector<ResampleTable> g_rs_tables;
@@ -70,14 +75,32 @@ static int get_resample_table(int orig, int nw, ResampleTable* out) {
   std::lock_guard<std::mutex> lock(g_rs_mutex);
   for (const ResampleTable& t : g_rs_tables)
     if (t.dev == dev && t.orig == orig && t.nw == nw) { *out = t; return MSA_OK; }
-  ResampleTable t{dev, orig, nw, 0, 0, nullptr};
+  ResampleTable t{dev, orig, nw, 0, 0, 0, nullptr, nullptr};
   std::vector<float> host;
   build_resample_kernel(orig, nw, &t.width, host);
   t.K = 2 * t.width + orig;
-  e = cudaMalloc(&t.kt, host.size() * sizeof(float));
+  // per phase: the run [lo, hi] of taps that are not exactly zero in fp32
+  std::vector<int> lo(nw, 0), hi(nw, -1);
+  for (int j = 0; j < nw; ++j) {
+    int a = t.K, b = -1;
+    for (int k = 0; k < t.K; ++k)
+      if (host[(size_t)k * nw + j] != 0.0f) { if (k < a) a = k; b = k; }
+    if (b < 0) { a = 0; b = 0; }
+    lo[j] = a; hi[j] = b;
+    if (b - a + 1 > t.run) t.run = b - a + 1;
+  }
+  std::vector<float> compact((size_t)t.run * nw, 0.0f);
+  for (int j = 0; j < nw; ++j) {
+    if (lo[j] + t.run > t.K) lo[j] = t.K - t.run;              // keep the run inside the staged span (extra taps are zeros)
+    for (int i = 0; i < t.run; ++i) compact[(size_t)i * nw + j] = host[(size_t)(lo[j] + i) * nw + j];
+  }
+  e = cudaMalloc(&t.kt, compact.size() * sizeof(float));
   if (e != cudaSuccess) return (int)e;
-  e = cudaMemcpy(t.kt, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice);
+  e = cudaMalloc(&t.first, (size_t)nw * sizeof(int));
   if (e != cudaSuccess) { cudaFree(t.kt); return (int)e; }
+  e = cudaMemcpy(t.kt, compact.data(), compact.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t.first, lo.data(), (size_t)nw * sizeof(int), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(t.kt); cudaFree(t.first); return (int)e; }
   g_rs_tables.push_back(t);
   *out = t;
   return MSA_OK;
@@ -91,7 +114,8 @@ __device__ __forceinline__ float load_sample(const int16_t* p) {
 // grid (frame tiles, B); FR frames per CTA (multiple of 4)
 template <class InT>
 __global__ void __launch_bounds__(256) resample_kernel(const InT* __restrict__ x, int L, int orig, int nw, int width, int K,
-                                                       const float* __restrict__ kt, float* __restrict__ y, int L_out, int FR) {
+                                                       int run, const float* __restrict__ kt, const int* __restrict__ first_tap,
+                                                       float* __restrict__ y, int L_out, int FR) {
   extern __shared__ float xs[];
   const int f0 = blockIdx.x * FR;
   const InT* xb = x + (size_t)blockIdx.y * L;
@@ -107,12 +131,13 @@ __global__ void __launch_bounds__(256) resample_kernel(const InT* __restrict__ x
   for (int w = threadIdx.x; w < FQ * nw; w += blockDim.x) {
     const int j = w % nw, fi = w / nw;
     float acc[kFrameTile] = {0.0f, 0.0f, 0.0f, 0.0f};
-    const float* xq = xs + fi * orig;
+    const float* xq = xs + fi * orig + __ldg(first_tap + j);
+    const float* kj = kt + j;
     const int qs = FQ * orig;                                // frames fi, fi + FQ, fi + 2 FQ, fi + 3 FQ
-    for (int k = 0; k < K; ++k) {
-      const float wt = __ldg(kt + (size_t)k * nw + j);
+    for (int i = 0; i < run; ++i) {                          // taps first[j] .. first[j] + run - 1, ascending like the dense sum
+      const float wt = __ldg(kj + (size_t)i * nw);
 #pragma unroll
-      for (int q = 0; q < kFrameTile; ++q) acc[q] = fmaf(wt, xq[q * qs + k], acc[q]);
+      for (int q = 0; q < kFrameTile; ++q) acc[q] = fmaf(wt, xq[q * qs + i], acc[q]);
     }
 #pragma unroll
     for (int q = 0; q < kFrameTile; ++q) {
@@ -142,7 +167,7 @@ static int launch_resample(const InT* x, int B, int L, int orig_freq, int new_fr
   const int n_frames = (int)((target + nw - 1) / nw);
   dim3 grid((n_frames + FR - 1) / FR, B);
   const size_t smem = (size_t)(FR * orig + t.K) * sizeof(float);
-  resample_kernel<InT><<<grid, 256, smem, st>>>(x, L, orig, nw, t.width, t.K, t.kt, y, L_out, FR);
+  resample_kernel<InT><<<grid, 256, smem, st>>>(x, L, orig, nw, t.width, t.K, t.run, t.kt, t.first, y, L_out, FR);
   note_launches(1);
   return (int)cudaGetLastError();
 }

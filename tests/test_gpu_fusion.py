@@ -87,6 +87,40 @@ def test_argmax_agreement_and_ragged_batches(impl):
     assert np.abs(l2.cpu().numpy() - fu.fuse_face_audio(sd, f[:300], a[:300])).max() < 1e-3
 
 
+@pytest.mark.parametrize("trained", [False, True], ids=["init", "trained"])
+def test_small_batches_matrix_vector_path(trained):
+    """Batches of 1..8 rows (the streaming path: one row per chunk) run as fp32 matrix-vector kernels
+    (csrc/msa_fusion_rows.cu).  Against the fp64 oracle: logits abs 1e-3, argmax equal; against the tensor-core
+    kernels forced onto the same rows: fp32 rounding; a row does not depend on the rows it is batched with."""
+    dev = need_gpu()
+    from msa_b200 import _lib
+    m, sd = _model(trained, 0)
+    (f, a, t), (fd, ad, td) = _inputs(8, dev)
+    ref3, ref2 = fu.fuse_all(sd, f, a, t), fu.fuse_face_audio(sd, f, a)
+    got = {}
+    for n in range(1, 9):
+        l3, a3 = m.fused_with_argmax(fd[:n], ad[:n], td[:n])
+        l3, a3 = l3.cpu().numpy(), a3.cpu().numpy()
+        l2, a2 = m.fused_with_argmax(fd[:n], ad[:n], None)
+        l2, a2 = l2.cpu().numpy(), a2.cpu().numpy()
+        assert l3.shape == (n, 7) and l2.shape == (n, 7)
+        assert np.abs(l3 - ref3[:n]).max() < 1e-3, (n, np.abs(l3 - ref3[:n]).max())
+        assert np.abs(l2 - ref2[:n]).max() < 1e-3, (n, np.abs(l2 - ref2[:n]).max())
+        assert np.array_equal(a3, ref3[:n].argmax(1)) and np.array_equal(a2, ref2[:n].argmax(1))
+        assert np.array_equal(a3, l3.argmax(1)) and np.array_equal(a2, l2.argmax(1))
+        got[n] = l3
+    for n in range(1, 8):
+        assert np.array_equal(got[n], got[8][:n]), n                    # batch == loop of rows, bit for bit
+    assert _lib.lib().msa_fusion_set_impl(2) == 0                       # tensor-core kernels for every batch size
+    try:
+        lt, at = m.fused_with_argmax(fd, ad, td)
+        torch.cuda.synchronize()
+        assert np.abs(lt.cpu().numpy() - got[8]).max() < 5e-4
+        assert np.array_equal(at.cpu().numpy(), got[8].argmax(1))
+    finally:
+        assert _lib.lib().msa_fusion_set_impl(0) == 0
+
+
 def test_tcgen05_matches_simt_on_device():
     dev = need_gpu()
     n = 2048
@@ -124,8 +158,8 @@ def test_full_size_fusion_batch_65536():
     sub = torch.from_numpy(np.sort(idx[:300])).to(dev)
     ls, _ = m0.fused_with_argmax(fd[sub].contiguous(), ad[sub].contiguous(), td[sub].contiguous())
     assert (ls - lt[sub]).abs().max().item() < 2e-5
-    l1, _ = m0.fused_with_argmax(fd[sub[:7]].contiguous(), ad[sub[:7]].contiguous(), td[sub[:7]].contiguous())
-    assert torch.equal(l1, ls[:7])
+    l1, _ = m0.fused_with_argmax(fd[sub[:9]].contiguous(), ad[sub[:9]].contiguous(), td[sub[:9]].contiguous())
+    assert torch.equal(l1, ls[:9])
     m1, _ = _model(True, 1)
     l1, _ = m1.fused_with_argmax(fd, ad, td)
     torch.cuda.synchronize()
