@@ -123,7 +123,8 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   // optional scratch table of mel dB values (see FeatParams::dbscratch); too small or absent: quads are recomputed
   P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
-  P.flags = flags;
+  static const int no_lockstep = env_int("MSA_FEAT_LOCKSTEP", 1) == 0 ? kFlagNoLockstep : 0;   // tuning knob (read once)
+  P.flags = flags | no_lockstep;
   P.parts = parts;
   const int threads = feat_threads();
   const FeatLayout lay = feat_layout(T, c, threads / 32);

@@ -60,7 +60,7 @@ constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (th
 constexpr int kClampCap = (kWarpBufBytes - kShareBytes) / 8;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
-enum : int { kFlagStrictNan = 1 };
+enum : int { kFlagStrictNan = 1, kFlagNoLockstep = 2 };
 
 struct FeatParams {
   const void* wav;       // [B, T] fp32 or int16
@@ -343,9 +343,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       for (int it = 0; it <= wper; ++it) {
         // the barrier is not needed for correctness: it keeps the warps of the CTA in the same code region
         // (the loop body is ~100 KB of SASS; warps drifting apart thrash the instruction cache)
-#ifndef MSA_NO_LOCKSTEP
-        env.sync();
-#endif
+        if (!(P.flags & kFlagNoLockstep)) env.sync();
         const int quad = wq_begin - 1 + it;
         if (quad < wq_first || quad >= wq_end) continue;
         const int f0 = 4 * quad;
@@ -654,10 +652,9 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
                 const int kk = (k == 0) ? 0 : kNfftM - k;
                 const c32 zk = zt[(k & 15) * kRow400 + (k >> 4)];
                 const c32 zn = zt[(kk & 15) * kRow400 + (kk >> 4)];
-                const float sx = zk.x + zn.x, sy = zk.y - zn.y;
-                const float dx = zk.x - zn.x, dy = zk.y + zn.y;
-                pa = 0.25f * fmaf(sx, sx, sy * sy);
-                pb = 0.25f * fmaf(dx, dx, dy * dy);
+                const c32 sm = add_conj(zk, zn), df = sub_conj(zk, zn);
+                pa = 0.25f * fmaf(sm.x, sm.x, sm.y * sm.y);
+                pb = 0.25f * fmaf(df.x, df.x, df.y * df.y);
               }
               pw[li][14 * h + 2 * i] = pa;
               pw[li][14 * h + 2 * i + 1] = pb;

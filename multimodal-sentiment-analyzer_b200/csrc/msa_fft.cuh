@@ -17,12 +17,47 @@
 
 namespace msa {
 
-struct alignas(8) c32 { float x, y; };   // 8-byte aligned: one LDS.64 / STS.64 per complex value
+struct alignas(8) c32 { float x, y; };   // 8-byte aligned: one LDS.64 / STS.64 per complex value, one register PAIR
+
+// ---- pair primitives ---------------------------------------------------------------------------
+// A complex value is a register pair, and sm_100a has packed fp32 arithmetic on pairs (FADD2 / FMUL2 /
+// FFMA2: two independent IEEE operations per instruction, one issue slot instead of two) whose pair
+// operand takes a half swap (LO_HI) and a sign per half as free modifiers, and whose other multiplicand
+// may be a scalar register or immediate broadcast to both halves.  That is exactly complex arithmetic:
+// a +- b, a +- i b, (a, i a) * s + c with a real s.  Every function below is two independent fp32
+// operations, written out per half for the CPU build (tests/emu) and as one packed instruction for the
+// device (same roundings: results do not depend on which form runs).  The kernel is bound by instruction
+// issue, so halving the butterfly instructions is worth ~1/4 of its run time (scripts/ubench/f32x2.cu).
+#if defined(__CUDA_ARCH__)
+MSA_FN float2 pk_f2(c32 a) { return make_float2(a.x, a.y); }
+MSA_FN c32 pk_c(float2 a) { return c32{a.x, a.y}; }
+MSA_FN c32 operator+(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), pk_f2(b))); }
+MSA_FN c32 operator-(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), make_float2(-b.x, -b.y))); }
+MSA_FN c32 add_mi(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), make_float2(b.y, -b.x))); }       // a - i b
+MSA_FN c32 add_pi(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), make_float2(-b.y, b.x))); }       // a + i b
+MSA_FN c32 add_conj(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), make_float2(b.x, -b.y))); }     // a + conj(b)
+MSA_FN c32 sub_conj(c32 a, c32 b) { return pk_c(__fadd2_rn(pk_f2(a), make_float2(-b.x, b.y))); }     // a - conj(b)
+MSA_FN c32 mul_s(c32 a, float s) { return pk_c(__fmul2_rn(pk_f2(a), make_float2(s, s))); }            // a s
+MSA_FN c32 fma_s(c32 a, float s, c32 c) { return pk_c(__ffma2_rn(pk_f2(a), make_float2(s, s), pk_f2(c))); }               // a s + c
+MSA_FN c32 fma_mi_s(c32 a, float s, c32 c) { return pk_c(__ffma2_rn(make_float2(a.y, -a.x), make_float2(s, s), pk_f2(c))); }  // (-i a) s + c
+MSA_FN c32 fma_pi_s(c32 a, float s, c32 c) { return pk_c(__ffma2_rn(make_float2(-a.y, a.x), make_float2(s, s), pk_f2(c))); }  // (i a) s + c
+MSA_FN c32 fms2(c32 e, c32 lo) { return pk_c(__ffma2_rn(pk_f2(e), make_float2(2.0f, 2.0f), make_float2(-lo.x, -lo.y))); }   // 2 e - lo
+#else
 MSA_FN c32 operator+(c32 a, c32 b) { return {a.x + b.x, a.y + b.y}; }
 MSA_FN c32 operator-(c32 a, c32 b) { return {a.x - b.x, a.y - b.y}; }
-MSA_FN c32 cmul(c32 a, c32 b) { return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
-MSA_FN c32 cmulc(c32 a, c32 b) { return {a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y}; }  // a * conj(b)
-template <bool INV> MSA_FN c32 rot90(c32 a) { return INV ? c32{-a.y, a.x} : c32{a.y, -a.x}; }  // * W4 (fwd: -i)
+MSA_FN c32 add_mi(c32 a, c32 b) { return {a.x + b.y, a.y - b.x}; }
+MSA_FN c32 add_pi(c32 a, c32 b) { return {a.x - b.y, a.y + b.x}; }
+MSA_FN c32 add_conj(c32 a, c32 b) { return {a.x + b.x, a.y - b.y}; }
+MSA_FN c32 sub_conj(c32 a, c32 b) { return {a.x - b.x, a.y + b.y}; }
+MSA_FN c32 mul_s(c32 a, float s) { return {a.x * s, a.y * s}; }
+MSA_FN c32 fma_s(c32 a, float s, c32 c) { return {fmaf(a.x, s, c.x), fmaf(a.y, s, c.y)}; }
+MSA_FN c32 fma_mi_s(c32 a, float s, c32 c) { return {fmaf(a.y, s, c.x), fmaf(-a.x, s, c.y)}; }
+MSA_FN c32 fma_pi_s(c32 a, float s, c32 c) { return {fmaf(-a.y, s, c.x), fmaf(a.x, s, c.y)}; }
+MSA_FN c32 fms2(c32 e, c32 lo) { return {fmaf(e.x, 2.0f, -lo.x), fmaf(e.y, 2.0f, -lo.y)}; }
+#endif
+// a b = a b.x + (i a) b.y   and   a conj(b) = a b.x + (-i a) b.y: the twiddle is the broadcast operand
+MSA_FN c32 cmul(c32 a, c32 b) { return fma_pi_s(a, b.y, mul_s(a, b.x)); }
+MSA_FN c32 cmulc(c32 a, c32 b) { return fma_mi_s(a, b.y, mul_s(a, b.x)); }
 
 // cos(pi * j / 16), j = 0..16
 template <int J> MSA_FN constexpr float cospi16() {
@@ -91,8 +126,10 @@ template <int I, int N, class F> MSA_FN void static_for(F&& f) {
 }
 
 template <bool INV> MSA_FN void dft4(c32& a, c32& b, c32& c, c32& d) {
-  c32 t0 = a + c, t1 = a - c, t2 = b + d, t3 = rot90<INV>(b - d);
-  a = t0 + t2; b = t1 + t3; c = t0 - t2; d = t1 - t3;
+  const c32 t0 = a + c, t1 = a - c, t2 = b + d, u = b - d;      // forward: * W4 = -i
+  a = t0 + t2; c = t0 - t2;
+  b = INV ? add_pi(t1, u) : add_mi(t1, u);
+  d = INV ? add_mi(t1, u) : add_pi(t1, u);
 }
 
 // Radix-2 butterfly with the twiddle folded into the multiply-adds:
@@ -102,23 +139,22 @@ template <bool INV> MSA_FN void dft4(c32& a, c32& b, c32& c, c32& d) {
 template <int K, bool INV> MSA_FN void bfly(c32 e, c32 o, c32& lo, c32& hi) {
   if constexpr (K == 0) {
     lo = e + o; hi = e - o;
-  } else if constexpr (K == 8) {
-    const c32 t = rot90<INV>(o);
-    lo = e + t; hi = e - t;
+  } else if constexpr (K == 8) {                                  // forward: o W = -i o
+    lo = INV ? add_pi(e, o) : add_mi(e, o);
+    hi = INV ? add_mi(e, o) : add_pi(e, o);
   } else if constexpr (K == 4 || K == 12) {
     constexpr float h = 0.70710678118654752440f;
-    // forward K=4: t = h (o.x + o.y, o.y - o.x); K=12: t = h (o.y - o.x, -(o.x + o.y)); inverse: conjugate twiddle
-    const float s = o.x + o.y, d = o.y - o.x;
-    float tx, ty;                       // t / h
-    if constexpr (K == 4) { tx = INV ? -d : s; ty = INV ? s : d; }
-    else { tx = INV ? -s : d; ty = INV ? -d : -s; }
-    lo = c32{fmaf(h, tx, e.x), fmaf(h, ty, e.y)};
-    hi = c32{fmaf(-h, tx, e.x), fmaf(-h, ty, e.y)};
+    const c32 u = add_mi(o, o);                                    // (o.x + o.y, o.y - o.x) = (1 - i) o
+    // o W / h:  K = 4 forward u, inverse i u;  K = 12 forward -i u, inverse -u
+    if constexpr (K == 4 && !INV) { lo = fma_s(u, h, e); hi = fma_s(u, -h, e); }
+    else if constexpr (K == 4 && INV) { lo = fma_mi_s(u, -h, e); hi = fma_mi_s(u, h, e); }
+    else if constexpr (K == 12 && !INV) { lo = fma_mi_s(u, h, e); hi = fma_mi_s(u, -h, e); }
+    else { lo = fma_s(u, -h, e); hi = fma_s(u, h, e); }
   } else {
     constexpr float c = cospi16<K>(), sn = sinpi16<K>();       // angle = pi K / 16
-    constexpr float s = INV ? -sn : sn;                        // forward w = (c, -sn): t = (o.x c + o.y sn, o.y c - o.x sn)
-    lo = c32{fmaf(o.y, s, fmaf(o.x, c, e.x)), fmaf(-o.x, s, fmaf(o.y, c, e.y))};
-    hi = c32{fmaf(2.0f, e.x, -lo.x), fmaf(2.0f, e.y, -lo.y)};
+    constexpr float s = INV ? -sn : sn;                        // forward w = (c, -sn): o w = o c + (-i o) sn
+    lo = fma_mi_s(o, s, fma_s(o, c, e));
+    hi = fms2(e, lo);
   }
 }
 
@@ -144,18 +180,16 @@ template <bool INV> MSA_FN void dft32(c32* v) { dft_pow2<32, INV>(v); }
 template <bool INV> MSA_FN void dft5(c32& v0, c32& v1, c32& v2, c32& v3, c32& v4) {
   constexpr float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
   constexpr float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
-  c32 a1 = v1 + v4, a2 = v2 + v3, d1 = v1 - v4, d2 = v2 - v3;
-  c32 y0 = {v0.x + a1.x + a2.x, v0.y + a1.y + a2.y};
-  c32 a = {v0.x + c1 * a1.x + c2 * a2.x, v0.y + c1 * a1.y + c2 * a2.y};
-  c32 b = {v0.x + c2 * a1.x + c1 * a2.x, v0.y + c2 * a1.y + c1 * a2.y};
-  c32 e = {s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y};
-  c32 g = {s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y};
+  const c32 a1 = v1 + v4, a2 = v2 + v3, d1 = v1 - v4, d2 = v2 - v3;
+  const c32 y0 = (v0 + a1) + a2;
+  const c32 a = fma_s(a2, c2, fma_s(a1, c1, v0));
+  const c32 b = fma_s(a2, c1, fma_s(a1, c2, v0));
+  const c32 e = fma_s(d2, s2, mul_s(d1, s1));
+  const c32 g = fma_s(d2, -s1, mul_s(d1, s2));
   // forward: y1 = a - i e, y4 = a + i e, y2 = b - i g, y3 = b + i g   (inverse: conjugate signs)
-  c32 ie = INV ? c32{-e.y, e.x} : c32{e.y, -e.x};
-  c32 ig = INV ? c32{-g.y, g.x} : c32{g.y, -g.x};
   v0 = y0;
-  v1 = a + ie; v4 = a - ie;
-  v2 = b + ig; v3 = b - ig;
+  v1 = INV ? add_pi(a, e) : add_mi(a, e); v4 = INV ? add_mi(a, e) : add_pi(a, e);
+  v2 = INV ? add_pi(b, g) : add_mi(b, g); v3 = INV ? add_mi(b, g) : add_pi(b, g);
 }
 
 // 25-point DFT, natural order in and out: n = 5a + b, k = c + 5d
@@ -167,8 +201,8 @@ template <bool INV> MSA_FN void dft25(c32* v) {
     static_for<1, 5>([&](auto cc) {
       constexpr int b = decltype(bc)::value, c = decltype(cc)::value;
       constexpr float wc = cos2pi25<b * c>(), ws = sin2pi25<b * c>();
-      const c32 a = v[5 * c + b];
-      v[5 * c + b] = INV ? c32{a.x * wc - a.y * ws, a.y * wc + a.x * ws} : c32{a.x * wc + a.y * ws, a.y * wc - a.x * ws};
+      const c32 a = v[5 * c + b];                                 // forward: a (wc, -ws) = a wc + (-i a) ws
+      v[5 * c + b] = fma_mi_s(a, INV ? -ws : ws, mul_s(a, wc));
     });
   });
 #pragma unroll
