@@ -116,7 +116,8 @@ FeatLayout feat_layout(int T, int nranks, int nwarps) {
   l.mfl_frames = 4 * ((((nFm + 3) / 4) + nranks - 1) / nranks);
   l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
   int buf = nwarps * kWarpBufBytes;
-  const int gather = (T / kAtom + 8) * 4;                      // rank 0 gathers all energy atoms there at the end
+  // rank 0 gathers all energy atoms and every rank's Partials there at the end
+  const int gather = (((T / kAtom + 8) * 4 + 15) & ~15) + 8 * (int)sizeof(Partials);
   if (buf < gather) buf = gather;
   l.buf_off = take(buf);
   // the MFCC rows share their region with the "pitch" phase's per-warp copy of the quad's input samples
@@ -886,18 +887,33 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
 
   // ---------------------------------------------------------------- rank 0: merge and assemble the row
   if (r == 0) {
-    // gather the energy atoms of all ranks (re-using the FFT tiles, idle by now)
+    // gather the energy atoms and the partial moments of all ranks (re-using the FFT tiles, idle by now) in ONE
+    // round of remote reads: which rank holds which atoms follows from (T, NR) alone, and the Partials are copied
+    // word by word, so no read waits for another (a serial walk over 8 ranks costs ~150 DSMEM round trips)
     float* all_atoms = reinterpret_cast<float*>(smem + lay.buf_off);
+    Partials* gathered = reinterpret_cast<Partials*>(smem + lay.buf_off + (((T / kAtom + 8) * 4 + 15) & ~15));
     int nA = 0;
-    for (int rr = 0; rr < NR; ++rr) {
-      const Partials* rp = env.remote(part, rr);
-      const float* ra = env.remote(atoms, rr);
-      const int n = rp->n_atoms;
+    if (P.parts & kPartWave) {
+      const int nGr = ceil_div(T, kGroup), gper_a = ceil_div(nGr, NR), full_atoms = T / kAtom;
+      nA = (nGr * 8 < full_atoms) ? nGr * 8 : full_atoms;
       env.lanes([&](int lane, int li) {
         (void)li;
-        for (int i = env.warp * 32 + lane; i < n; i += env.nthreads) all_atoms[nA + i] = ra[i];
+        for (int a = env.warp * 32 + lane; a < nA; a += env.nthreads) {
+          const int rr = a / (8 * gper_a);
+          all_atoms[a] = env.remote(atoms, rr)[a - 8 * gper_a * rr];
+        }
       });
-      nA += n;
+    }
+    {
+      constexpr int kWords = (int)(sizeof(Partials) / 8);
+      static_assert(sizeof(Partials) % 8 == 0, "Partials is copied as 8-byte words");
+      env.lanes([&](int lane, int li) {
+        (void)li;
+        for (int i = env.warp * 32 + lane; i < NR * kWords; i += env.nthreads) {
+          const int rr = i / kWords, w = i - rr * kWords;
+          reinterpret_cast<double*>(gathered + rr)[w] = reinterpret_cast<const double*>(env.remote(part, rr))[w];
+        }
+      });
     }
     env.sync();
     // rhythm: frame energies e_g = sum of 5 atoms at stride 2 (400 = 5*80, 160 = 2*80)
@@ -937,7 +953,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       Partials tot = *part;
 #pragma unroll 1
       for (int rr = 1; rr < NR; ++rr) {
-        const Partials* rp = env.remote(part, rr);
+        const Partials* rp = gathered + rr;
 #pragma unroll 1
         for (int k = 0; k < kMfcc; ++k) tot.mf_sum[k] += rp->mf_sum[k];
         tot.mf_sumsq += rp->mf_sumsq; tot.mf_abs_lo += rp->mf_abs_lo; tot.mf_abs_hi += rp->mf_abs_hi;
