@@ -348,7 +348,7 @@ def run_native(args):
             "roofline": {"bound": "hbm", "kernel": "features_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(S), "traffic_unit": "bytes per launch (ncu dram read+write)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SEGMENT * S, "peak_source": peak_src,
-                         "ms_per_launch": ms_feat, "note": "bound by fp32 instruction issue (register FFTs: ~58 FLOP per waveform byte vs a ridge of ~11), not by HBM: ncu smsp__issue_active 57 %, see DESIGN.md 4.1"},
+                         "ms_per_launch": ms_feat, "note": "bound by fp32 arithmetic (register FFTs: ~58 FLOP per waveform byte vs a ridge of ~11), not by HBM: ncu FMA pipe 42 % busy, issue slots 46 %, see DESIGN.md 4.1"},
             "kernels_ms": {"features": ms_feat, "fusion_chain": ms_fus},
             "fusion_tensor": (lambda pk: {"bound": "tensor", "achieved": 9069568.0 * S / (ms_fus / 1000.0) / 1e12, "peak": pk[0], "unit": "TFLOP/s",
                                           "frac": 9069568.0 * S / (ms_fus / 1000.0) / 1e12 / pk[0], "peak_source": pk[1],

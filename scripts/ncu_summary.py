@@ -5,7 +5,7 @@ hdr, units = rows[0], rows[1]
 want = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__occupancy_limit',
         'launch__shared_mem_per_block', 'launch__grid_size', 'launch__block_size', 'launch__cluster',
-        'smsp__inst_executed.sum', 'sm__inst_executed_pipe_fma', 'sm__inst_executed_pipe_alu', 'sm__inst_executed_pipe_lsu',
+        'smsp__inst_executed.sum', 'sm__inst_executed_pipe_fma', 'sm__pipe_fma', 'sm__inst_executed_pipe_alu', 'sm__inst_executed_pipe_lsu',
         'sm__inst_executed_pipe_fp64', 'sm__inst_executed_pipe_xu', 'sm__inst_executed_pipe_tensor', 'sm__pipe_tensor',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared',
         'smsp__issue_active.avg.pct', 'sm__throughput.avg.pct', 'l1tex__throughput.avg.pct', 'lts__throughput.avg.pct',
