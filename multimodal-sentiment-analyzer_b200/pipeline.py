@@ -101,18 +101,19 @@ class SegmentPipeline:
     def run_host(self, pcm_host: torch.Tensor, face_host: torch.Tensor, text_host: Optional[torch.Tensor],
                  rows_host: torch.Tensor, first_id: int = 0, chunk: int = 128) -> torch.Tensor:
         """Same as ``run`` for HOST buffers (pinned: int16 PCM [n, T], face [n, 27], text [n, 783] or None).
-        The PCM is cut into chunks of `chunk` segments: a copy stream uploads chunk i+1 into the other half of
-        a double buffer while the compute stream runs the feature kernel on chunk i (the upload is the
+        The PCM is cut into chunks of `chunk` segments: a copy stream uploads chunk i+1 into the next slot of
+        a ring of three staging buffers while the compute stream runs the feature kernel on chunk i (the upload is the
         longer of the two: 160 KB per segment over PCIe).  The face / text rows go up once, the fusion chain
         runs once over all n rows when the last chunk's features are done, and the [n, 40] result table comes
         back with one device->host copy into `rows_host` (pinned).  The returned device table and `rows_host`
-        are valid once the current stream has been synchronised."""
+        are valid once the current stream has been synchronised.  Calls pipeline with each other: every staging
+        buffer is guarded by its own event (the kernel that last read it), so the first upload of a call starts
+        while the previous call's last kernels are still running and the copy engine never idles between calls."""
         n, T = pcm_host.shape
         dev = self.device
         cur = torch.cuda.current_stream(dev)
         st = self._host_state(chunk, T, text_host is not None, n)
         copy_s = st["copy_stream"]
-        copy_s.wait_stream(cur)                                   # buffers of the previous call are free
         audio_rows = st["audio"][:n]
         # chunk boundaries; the last chunk is cut short so that little compute is left once the upload ends
         bounds = list(range(0, n, chunk)) + [n]
@@ -122,7 +123,8 @@ class SegmentPipeline:
         side = None
         for i in range(len(bounds) - 1):
             b, e = bounds[i], bounds[i + 1]
-            k = i & 1
+            k = st["next"]                                        # staging ring position, carried across calls
+            st["next"] = (k + 1) % len(st["pcm"])
             with torch.cuda.stream(copy_s):
                 if st["free"][k] is not None:
                     copy_s.wait_event(st["free"][k])              # the kernel that read this half is done
@@ -130,6 +132,8 @@ class SegmentPipeline:
                 up = torch.cuda.Event()
                 up.record(copy_s)
                 if i == 0:                                        # small side inputs ride behind the first chunk
+                    if st["side_free"] is not None:
+                        copy_s.wait_event(st["side_free"])        # the previous call's fusion has read them
                     st["face"][:n].copy_(face_host, non_blocking=True)
                     if text_host is not None:
                         st["text"][:n].copy_(text_host, non_blocking=True)
@@ -143,6 +147,8 @@ class SegmentPipeline:
         cur.wait_event(side)
         text = st["text"][:n] if text_host is not None else None
         logits, amax = self.fusion.fused_with_argmax(st["face"][:n], audio_rows, text)
+        st["side_free"] = torch.cuda.Event()
+        st["side_free"].record(cur)
         rows = pack_rows(audio_rows, logits, amax, first_id)
         rows_host[:n].copy_(rows, non_blocking=True)
         return rows
@@ -152,8 +158,11 @@ class SegmentPipeline:
         st = getattr(self, "_hs", None)
         if st is None or st["key"] != key or st["audio"].shape[0] < n:
             dev = self.device
-            st = {"key": key, "copy_stream": torch.cuda.Stream(dev), "free": [None, None],
-                  "pcm": [torch.empty(chunk, T, dtype=torch.int16, device=dev) for _ in range(2)],
+            if st is not None:
+                torch.cuda.current_stream(dev).synchronize()      # the old buffers may still be in use
+                st["copy_stream"].synchronize()
+            st = {"key": key, "copy_stream": torch.cuda.Stream(dev), "free": [None] * 3, "side_free": None, "next": 0,
+                  "pcm": [torch.empty(chunk, T, dtype=torch.int16, device=dev) for _ in range(3)],
                   "face": torch.empty(n, 27, device=dev),
                   "text": torch.empty(n, 783, device=dev) if with_text else None,
                   "audio": torch.empty(n, 31, device=dev)}

@@ -235,12 +235,38 @@ def test_host_buffer_pipeline_equals_resident():
     pipe = msa_b200.SegmentPipeline(ana, m)
     for tx in (text, None):
         out = torch.zeros(n, ROW_WORDS).pin_memory()
-        for _ in range(2):                                   # second pass re-uses the double buffer
+        for _ in range(2):                                   # second pass re-uses the staging ring
             pipe.run_host(pcm, face, tx, out, first_id=7, chunk=8)
         torch.cuda.synchronize()
         ref = pipe.run(pcm.to(dev), face.to(dev), None if tx is None else tx.to(dev), first_id=7)
         torch.cuda.synchronize()
         assert torch.equal(out.view(torch.int32), ref.cpu().view(torch.int32))
+
+
+def test_host_buffer_pipeline_back_to_back_calls():
+    """Consecutive run_host calls overlap (the next call's uploads start while the previous call's kernels still
+    run; every staging buffer is guarded by its own event): four calls with DIFFERENT inputs issued without a
+    synchronise in between give the tables of the resident path."""
+    dev = need_gpu()
+    import msa_b200
+    from msa_b200.pipeline import ROW_WORDS
+    ana = msa_b200.AudioAnalyzer(device="cuda:0")
+    m, _ = _model(True, 0)
+    n = 37
+    pipe = msa_b200.SegmentPipeline(ana, m)
+    ins, outs = [], []
+    for c in range(4):
+        ins.append((torch.from_numpy(synth.fast_segments_pcm(50 + c, n)).pin_memory(),
+                    torch.from_numpy(synth.face_rows(60 + c, n)).pin_memory(),
+                    torch.from_numpy(synth.text_rows(70 + c, n)).pin_memory()))
+        outs.append(torch.zeros(n, ROW_WORDS).pin_memory())
+    for c in range(4):
+        pipe.run_host(*ins[c], outs[c], first_id=100 * c, chunk=8)
+    torch.cuda.synchronize()
+    for c in range(4):
+        ref = pipe.run(*(t.to(dev) for t in ins[c]), first_id=100 * c)
+        torch.cuda.synchronize()
+        assert torch.equal(outs[c].view(torch.int32), ref.cpu().view(torch.int32)), c
 
 
 @pytest.mark.parametrize("use_graph,with_text", [(False, False), (True, False), (True, True)])
