@@ -162,16 +162,23 @@ MSA_FN double red_comb(int op, double a, double b) {
 }
 
 // Deterministic block reduction of K per-lane doubles: out[k] (shared memory) = op_k over all threads.
-// Level 1 is the Env's warp reduction (shuffles on the GPU), level 2 combines the per-warp values.
+// Level 1 (reduce_warp_stage) is the Env's warp reduction (shuffles on the GPU) into the warp's scratch slots
+// slot0 .. slot0 + K - 1, level 2 (reduce_block_stage) combines the per-warp values of slots 0 .. K - 1 behind a
+// barrier.  The two levels can be apart: a phase deposits its per-warp values without a barrier and a later
+// phase's reduction picks them up.
 template <int K, class Env, class Get>
-MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, Get get) {
-  static_assert(K <= kRedSlots, "reduction scratch");
+MSA_KFN void reduce_warp_stage(Env& env, double* wred, int slot0, const int* ops, Get get) {
   const int NW = env.nwarps;
 #pragma unroll
   for (int k = 0; k < K; ++k) {
     const double r = env.warp_reduce(ops[k], [&](int li) { return get(li, k); });
-    env.lanes([&](int lane, int li) { (void)li; if (lane == 0) wred[k * NW + env.warp] = r; });
+    env.lanes([&](int lane, int li) { (void)li; if (lane == 0) wred[(slot0 + k) * NW + env.warp] = r; });
   }
+}
+template <int K, class Env>
+MSA_KFN void reduce_block_stage(Env& env, double* wred, double* out, const int* ops) {
+  static_assert(K <= kRedSlots, "reduction scratch");
+  const int NW = env.nwarps;
   env.sync();
   if (env.warp == 0) {
     env.lanes([&](int lane, int li) {
@@ -184,6 +191,11 @@ MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, G
     });
   }
   env.sync();
+}
+template <int K, class Env, class Get>
+MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, Get get) {
+  reduce_warp_stage<K>(env, wred, 0, ops, get);
+  reduce_block_stage<K>(env, wred, out, ops);
 }
 
 template <class Env, class InT>
@@ -301,14 +313,13 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         e_noi[li] = acc;
       });
     }
+    // per-warp totals go to scratch slots 4..7 WITHOUT a barrier: every warp moves on to its STFT-512 quads as
+    // soon as its own loads are in (this phase is pure load latency), and the block-level sums are formed together
+    // with the residual's, behind that phase's barrier
     const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
+    reduce_warp_stage<4>(env, wred, 4, ops, [&](int li, int k) {
       return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
     });
-    if (env.tid == 0) {
-      part->e_total = rout[0]; part->e_noise = rout[1]; part->e_left = rout[2]; part->a_max = (float)rout[3];
-      part->n_atoms = n_atoms_local;
-    }
   }
 
   // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual
@@ -468,11 +479,16 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         }
       }
     }
-    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
+    const int ops[8] = {kOpSum, kOpSum, kOpSum, kOpMax, kOpSum, kOpSum, kOpSum, kOpMax};
+    reduce_warp_stage<4>(env, wred, 0, ops, [&](int li, int k) {
       return k == 0 ? ps[li] : (k == 1 ? pq[li] : (k == 2 ? pn[li] : (double)pmax[li]));
     });
-    if (env.tid == 0) { part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3]; }
+    reduce_block_stage<8>(env, wred, rout, ops);          // slots 4..7: the wave-statistics totals deposited above
+    if (env.tid == 0) {
+      part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3];
+      part->e_total = rout[4]; part->e_noise = rout[5]; part->e_left = rout[6]; part->a_max = (float)rout[7];
+      part->n_atoms = n_atoms_local;
+    }
   }
 
   // ---------------------------------------------------------------- K2: STFT-400 -> power -> mel -> dB -> DCT shares
