@@ -175,8 +175,10 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------ GPU arm
 def run_native(args):
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # keeps "NCCL version ..." off stdout: one JSON line only
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # NCCL prints its "NCCL version ..." banner (any NCCL_DEBUG level from VERSION up) on stdout when the first
+    # communicator is created; stdout must carry ONE JSON line.  Send NCCL's log to stderr, and, because a pod may
+    # pin NCCL_DEBUG_FILE itself, also point file descriptor 1 at stderr until the first collective has run.
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -188,7 +190,18 @@ def run_native(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(8, device=dev)
+            dist.all_reduce(warm)                                      # creates the communicator (and prints the banner)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     if not os.path.exists(os.path.join(ROOT, "multimodal-sentiment-analyzer_b200", "libmsa_b200.so")):
         if local == 0:
             entry.build()
