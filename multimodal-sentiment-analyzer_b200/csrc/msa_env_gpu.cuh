@@ -30,6 +30,10 @@ struct GpuEnv {
     return __fmaf_rn(__int_as_float(0x4B400000 + v), 1.0f / 32768.0f, -384.0f);
   }
   __device__ __forceinline__ float ld(const int16_t* p) { return s16_to_f32((int)__ldg(p)); }
+  // the same for the LAST pass over a segment (the MFCC frames): evict-first, so that lines nobody will read again
+  // leave L2 before the live segments of the other 295 CTAs do
+  __device__ __forceinline__ float ld_last(const float* p) { return __ldcs(p); }
+  __device__ __forceinline__ float ld_last(const int16_t* p) { return s16_to_f32((int)__ldcs(p)); }
 
   // samples idx .. idx+3 of a segment of T samples (0 beyond the end), one vector load when aligned
   __device__ __forceinline__ void ld4(const float* x, int idx, int T, float* v) {

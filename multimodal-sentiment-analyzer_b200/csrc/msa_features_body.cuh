@@ -620,7 +620,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               float raw[24];                                       // (sharing the quad's 40 samples between the two FFTs costs more in registers than the 8 loads it saves)
               if (interior) {
   #pragma unroll
-                for (int i = 0; i < 24; ++i) raw[i] = env.ld(x + sb + 25 * i + lane);
+                for (int i = 0; i < 24; ++i) raw[i] = env.ld_last(x + sb + 25 * i + lane);
               } else {
   #pragma unroll
                 for (int i = 0; i < 24; ++i) raw[i] = xr(sb + 25 * i + lane);
