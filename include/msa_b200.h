@@ -33,6 +33,11 @@ extern "C" {
 
 /* flags of msa_features_* */
 #define MSA_FEAT_STRICT_NAN 1 /* mono intensity = NaN exactly like audio_analyzer.py:194-196 (default) */
+#define MSA_FEAT_NO_LOCKSTEP 2 /* tuning: no per-quad block barrier in the STFT-512 phase (also MSA_FEAT_LOCKSTEP=0) */
+#define MSA_FEAT_FOLD_WAVE 4 /* opt-in (also MSA_FEAT_FOLD=1 in the environment): the wave statistics (rhythm, speech_rate,
+                              * snr, consistency) are formed by the STFT-512 quads from the samples they hold anyway, instead of
+                              * a pass of their own over the segment: one read of the waveform fewer, bit-identical results.
+                              * Applies when parts has both MSA_PART_WAVE and MSA_PART_PITCH; detail[79] = 1 for rows it produced. */
 /* parts mask: which feature groups to compute (the rest take the reference's exception defaults) */
 #define MSA_PART_WAVE 1  /* rhythm, speech_rate, snr, consistency */
 #define MSA_PART_MFCC 2  /* timbre, clarity */
@@ -65,7 +70,8 @@ int msa_features_smem_bytes(int T, int cluster_size);
  *   detail  [B, 96] out or NULL: [0:27] raw features before LayerNorm in analyze()'s concat order
  *           (emotion8, pitch, intensity, timbre13, speech_rate, rhythm3), [27:31] the four quality
  *           floats, [32:63] the full LayerNorm(31) row (NaN where the reference is NaN),
- *           [64:77] diagnostics (top_db max, residual mean/std/max, energies, counts, clamped-pass flag, min dB)
+ *           [64:80] diagnostics (top_db max, residual mean/std/max, energies, counts, clamped-pass flag, min dB,
+ *           candidate level, clamp flag, [79] = 1 if MSA_FEAT_FOLD_WAVE produced the row)
  *   dbg_mfcc [B, T/200+1, 13] out or NULL: the MFCC matrix (frames x coefficients)
  *   cluster_size 0 = auto, else 1/2/4/8
  */

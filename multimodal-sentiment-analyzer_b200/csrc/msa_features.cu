@@ -9,7 +9,7 @@
 
 namespace msa {
 
-template <class InT, int THREADS>
+template <class InT, int THREADS, bool FOLD = false>
 __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) features_kernel(const FeatParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) features_kern
   env.rank = (int)cluster.block_rank();
   env.nranks = (int)cluster.num_blocks();
   env.cluster_id = blockIdx.x / env.nranks;
-  features_cta<GpuEnv, InT>(env, P, smem);
+  features_cta<GpuEnv, InT, FOLD>(env, P, smem);
 }
 
 static std::mutex g_tab_mutex;
@@ -124,13 +124,20 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
   static const int no_lockstep = env_int("MSA_FEAT_LOCKSTEP", 1) == 0 ? kFlagNoLockstep : 0;   // tuning knob (read once)
-  P.flags = flags | no_lockstep;
+  // opt-in (flag bit 4 or MSA_FEAT_FOLD=1, read once): the wave statistics ride on the STFT-512 quads instead of
+  // making their own pass over the segment (features_cta<.., FOLD>; bit-identical results).  Needs both parts and the
+  // 256-thread CTA; otherwise the separate pass runs.
+  static const int fold_env = env_int("MSA_FEAT_FOLD", 0) != 0 ? kFlagFoldWave : 0;
+  P.flags = flags | no_lockstep | fold_env;
   P.parts = parts;
   const int threads = feat_threads();
-  const FeatLayout lay = feat_layout(T, c, threads / 32);
+  bool fold = (P.flags & kFlagFoldWave) && (parts & kPartWave) && (parts & kPartPitch) && threads == 256;
+  if (fold && feat_layout(T, c, threads / 32, true).total > kMaxSmem) fold = false;
+  const FeatLayout lay = feat_layout(T, c, threads / 32, fold);
   if (lay.total > kMaxSmem) return MSA_ERR_UNSUPPORTED_LENGTH;
 
-  auto kern = (threads == 256) ? features_kernel<InT, 256> : features_kernel<InT, 512>;
+  auto kern = fold ? features_kernel<InT, 256, true>
+                   : ((threads == 256) ? features_kernel<InT, 256> : features_kernel<InT, 512>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};

@@ -60,7 +60,7 @@ constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (th
 constexpr int kClampCap = (kWarpBufBytes - kShareBytes) / 8;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
-enum : int { kFlagStrictNan = 1, kFlagNoLockstep = 2 };
+enum : int { kFlagStrictNan = 1, kFlagNoLockstep = 2, kFlagFoldWave = 4 };   // kFlagFoldWave: see features_cta<.., FOLD>
 
 struct FeatParams {
   const void* wav;       // [B, T] fp32 or int16
@@ -103,18 +103,51 @@ MSA_FN float int_as_float(int v) {
 #endif
 }
 
+// STFT-512 quads (4 frames each) of a segment, and how many of them a rank of the cluster takes
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int pitch_quads(int T) {
+  const int nFp = T / kHopP + 1;
+  const int nBl = (T - 1 + kNfftP / 2) / kHopP + 1;
+  return ((nFp > nBl ? nFp : nBl) + 3) / 4;
+}
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int fold_quads_per_rank(int T, int nranks) { return (pitch_quads(T) + nranks - 1) / nranks; }
+// FOLD: energy atom a (samples 80 a .. 80 a + 79, entries 20 a .. 20 a + 19; the ragged last one ends with the segment)
+// is finished by the quad whose 512 own samples (t = 512 q - 256 ..) hold its last entry
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int fold_last_entry(int a, int T) { const int e = 20 * a + 19, m = (T - 1) >> 2; return e < m ? e : m; }
+inline
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+int fold_first_atom_of_quad(int q0) { return q0 <= 0 ? 0 : (128 * q0 - 83 + 19) / 20; }   // smallest a with (20 a + 83) >> 7 >= q0
+
 // identical on host (launch configuration) and device (carve-up)
 inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-FeatLayout feat_layout(int T, int nranks, int nwarps) {
+FeatLayout feat_layout(int T, int nranks, int nwarps, bool fold = false) {
   FeatLayout l;
   int off = 0;
   auto take = [&](int bytes) { int o = off; off += (bytes + 15) & ~15; return o; };
   const int nFm = T / kHopM + 1;
   l.mfl_frames = 4 * ((((nFm + 3) / 4) + nranks - 1) / nranks);
   l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
+  if (fold) {
+    // FOLD: a rank holds the atoms that END in its STFT-512 quads (128 entries of 4 samples per quad, 20 per atom)
+    const int cap = (128 * fold_quads_per_rank(T, nranks)) / 20 + 2;
+    if (l.atoms_cap < cap) l.atoms_cap = cap;
+  }
   int buf = nwarps * kWarpBufBytes;
   // rank 0 gathers all energy atoms and every rank's Partials there at the end
   const int gather = (((T / kAtom + 8) * 4 + 15) & ~15) + 8 * (int)sizeof(Partials);
@@ -198,12 +231,17 @@ MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, G
   reduce_block_stage<K>(env, wred, out, ops);
 }
 
-template <class Env, class InT>
+// FOLD = true (kFlagFoldWave; needs both the wave and the pitch part): no separate wave-statistics pass.  The 512
+// own samples of every STFT-512 quad sit in the warp's `xs` tile anyway, so the quad squares them into the SAME
+// 4-sample entries, sums the SAME 20 entries per energy atom in the same order (an atom that straddles two quads is
+// carried as its running sum) and adds the same totals: the segment is read twice instead of three times and the
+// results are bit-identical to the separate pass (fp64 totals are summed in another order).
+template <class Env, class InT, bool FOLD = false>
 MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   constexpr int S = Env::kStates;           // per-lane state copies: 1 on the GPU (registers), 32 in the CPU emulation
   const int T = P.T;
   const int seg = env.cluster_id, r = env.rank, NR = env.nranks, NW = env.nwarps;
-  const FeatLayout lay = feat_layout(T, NR, NW);
+  const FeatLayout lay = feat_layout(T, NR, NW, FOLD);
   const InT* x = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T;
 
   c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
@@ -233,7 +271,11 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   // groups of 640 samples (8 atoms of 80): lane l loads float4 j at sample 128 j + 4 l, a 160-entry
   // shared-memory tile per group turns the per-lane partial sums into per-atom sums (20 entries each)
   int n_atoms_local = 0;
-  {
+  // FOLD: the same totals, accumulated by the STFT-512 quads below
+  double f_tot[S], f_noi[S], f_left[S];
+  float f_amax[S], f_carry[S];
+  for (int i = 0; i < S; ++i) { f_tot[i] = f_noi[i] = f_left[i] = 0.0; f_amax[i] = f_carry[i] = 0.0f; }
+  if constexpr (!FOLD) {
     double e_tot[S], e_noi[S], e_left[S];
     float a_max[S];
     for (int i = 0; i < S; ++i) { e_tot[i] = e_noi[i] = e_left[i] = 0.0; a_max[i] = 0.0f; }
@@ -477,7 +519,77 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
             pmax[li] = fmaxf(pmax[li], mx);
           });
         }
+        if constexpr (FOLD) {
+          // wave statistics of the quad's own 512 samples t = 512 quad - 256 + k (still in xs; the FFT tiles are free and
+          // serve as scratch): entries e = E0 .. E0 + 127 of 4 samples each, exactly the entries of the separate pass
+          float* ent = reinterpret_cast<float*>(wbuf);
+          const int E0 = 128 * quad - 64;
+          const bool owned = quad >= wq_begin;                   // the warm-up quad only starts the straddling atom
+          const bool clean = (s0 >= 0) && (s0 + kNfftP <= T);
+          const int nn = P.noise_n;
+          const bool noisy = owned && (4 * E0 < nn || 4 * E0 + kNfftP > T - nn);
+          env.lanes([&](int lane, int li) {
+            double tot = 0.0, noi = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const int m = lane + 32 * c;
+              const float4 q4 = *reinterpret_cast<const float4*>(xs + 4 * m);
+              float q[4] = {q4.x, q4.y, q4.z, q4.w};
+              const int t = 4 * (E0 + m);
+              if (!clean) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (t + i < 0 || t + i >= T) q[i] = 0.0f;      // xs holds the reflect padding there
+              }
+              const float sq = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
+              ent[m] = sq;
+              tot += (double)sq;
+              if (noisy) {
+                // first and last int(0.05 T) samples (audio_analyzer.py:282-285): exact squares summed in fp64
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (t + i < nn || t + i >= T - nn) noi += (double)q[i] * (double)q[i];
+              }
+            }
+            if (owned) { f_tot[li] += tot; f_noi[li] += noi; }
+          });
+          env.wsync();
+          // lane l < 8 continues / forms the l-th atom that overlaps the quad: a sequential fp32 sum over its entries
+          const int full_atoms = T / kAtom;
+          const int a_first = (E0 > 0) ? E0 / 20 : 0;
+          const int a_base = fold_first_atom_of_quad(q_begin);   // first atom this rank stores
+          const bool have_prev = quad > wq_first;                // the previous quad of this warp left its carry
+          env.lanes([&](int lane, int li) {
+            const int a = a_first + lane;
+            const int last = fold_last_entry(a, T);
+            const int lo = (20 * a > E0) ? 20 * a : E0;
+            const int hi = (last < E0 + 127) ? last : E0 + 127;
+            if (lane < 8 && a <= full_atoms && lo <= hi) {
+              float s = (20 * a < E0 && have_prev) ? f_carry[li] : 0.0f;
+              for (int e = lo; e <= hi; ++e) s += ent[e - E0];
+              if (hi < last) {
+                ent[128] = s;                                    // the atom goes on in the next quad
+              } else if (owned) {
+                if (a < full_atoms) {
+                  atoms[a - a_base] = s;
+                  f_amax[li] = fmaxf(f_amax[li], s);
+                } else {
+                  f_left[li] += (double)s;                       // the T mod 80 samples behind the last full atom
+                }
+              }
+            }
+          });
+          env.wsync();
+          env.lanes([&](int lane, int li) { (void)lane; f_carry[li] = ent[128]; });
+          env.wsync();                                           // the tiles are free again
+        }
       }
+    }
+    if constexpr (FOLD) {
+      const int opsw[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
+      reduce_warp_stage<4>(env, wred, 4, opsw, [&](int li, int k) {
+        return k == 0 ? f_tot[li] : (k == 1 ? f_noi[li] : (k == 2 ? f_left[li] : (double)f_amax[li]));
+      });
     }
     const int ops[8] = {kOpSum, kOpSum, kOpSum, kOpMax, kOpSum, kOpSum, kOpSum, kOpMax};
     reduce_warp_stage<4>(env, wred, 0, ops, [&](int li, int k) {
@@ -915,8 +1027,14 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       env.lanes([&](int lane, int li) {
         (void)li;
         for (int a = env.warp * 32 + lane; a < nA; a += env.nthreads) {
-          const int rr = a / (8 * gper_a);
-          all_atoms[a] = env.remote(atoms, rr)[a - 8 * gper_a * rr];
+          if constexpr (FOLD) {
+            const int qpr = fold_quads_per_rank(T, NR);
+            const int rr = ((20 * a + 83) >> 7) / qpr;             // the rank whose quad finished the atom
+            all_atoms[a] = env.remote(atoms, rr)[a - fold_first_atom_of_quad(rr * qpr)];
+          } else {
+            const int rr = a / (8 * gper_a);
+            all_atoms[a] = env.remote(atoms, rr)[a - 8 * gper_a * rr];
+          }
         }
       });
     }
@@ -1090,6 +1208,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
 #pragma unroll 1
         for (int k = 79; k < kDetailStride; ++k) d[k] = 0.0f;
+        if constexpr (FOLD) d[79] = 1.0f;                  // which variant produced the row
       }
     }
   }

@@ -96,7 +96,9 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
   FeatParams P{};
   P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.noise_n = (int)(0.05 * (double)T);
   P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.dbscratch = dbscratch; P.tab = &tab; P.flags = flags; P.parts = parts;
-  const FeatLayout lay = feat_layout(T, nranks, nwarps);
+  // kFlagFoldWave: the wave statistics ride on the STFT-512 quads (needs both parts), like the launcher decides it
+  const bool fold = (flags & kFlagFoldWave) && (parts & kPartWave) && (parts & kPartPitch);
+  const FeatLayout lay = feat_layout(T, nranks, nwarps, fold);
   for (int seg = 0; seg < B; ++seg) {
     CpuCluster cl(nranks * nwarps);
     std::vector<std::unique_ptr<unsigned char[]>> mem;
@@ -112,8 +114,13 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
       for (int w = 0; w < nwarps; ++w)
         th.emplace_back([&, r, w]() {
           CpuEnv env{w * 32, nwarps * 32, 0, w, nwarps, r, nranks, seg, bars[r].get(), &cl};
-          if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
-          else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
+          if (fold) {
+            if (is_s16) features_cta<CpuEnv, int16_t, true>(env, P, cl.smem[r]);
+            else features_cta<CpuEnv, float, true>(env, P, cl.smem[r]);
+          } else {
+            if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
+            else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
+          }
         });
     for (auto& t : th) t.join();
   }

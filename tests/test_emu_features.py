@@ -169,3 +169,38 @@ def test_results_do_not_depend_on_the_partition(emu, name):
             assert np.array_equal(cur[2], ref[2]), (nranks, nwarps)
     if name == "path_flip":
         assert (1.0, 0.0) in paths and (1.0, 1.0) in paths           # both the patch-list and the clamped-pass path ran
+
+
+@pytest.mark.parametrize("case", ["seg1234", "half_silence", "odd_12345", "short_500", "T257", "T513", "T30001", "T80129", "T79920"])
+def test_fold_wave_statistics_into_the_stft_quads(emu, case):
+    """MSA_FEAT_FOLD_WAVE (flag 4): the STFT-512 quads form the energy atoms, totals and noise energy from the samples
+    they hold, instead of the separate wave-statistics pass.  Entries, atoms and their summation order are the same, so
+    every output (rows, raw features, LayerNorm row, MFCC matrix, diagnostics) must be bit-identical for every segment
+    length (ragged last atom, atoms straddling quads, warps and ranks) and cluster shape; detail[79] tells the variant."""
+    if case == "seg1234":
+        x = synth.pcm_to_f32(synth.segment_pcm(1234))
+    elif case.startswith("T"):
+        x = synth.pcm_to_f32(synth.segment_pcm(77, int(case[1:])))
+    else:
+        x = synth.adversarial_cases()[case]
+    for nranks, nwarps in ((1, 8), (2, 4), (4, 3), (8, 8), (1, 2)):
+        f0, d0, g0 = run(emu, x[None], nranks, nwarps, flags=1)
+        f1, d1, g1 = run(emu, x[None], nranks, nwarps, flags=1 | 4)
+        assert d0[0, 79] == 0.0 and d1[0, 79] == 1.0
+        assert np.array_equal(f0, f1)
+        assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True), (nranks, nwarps)
+        assert np.array_equal(g0, g1)
+    # int16 ingest takes the same route
+    pcm = np.round(x * 32768.0).astype(np.int16)
+    f2, d2, _ = run(emu, pcm[None], 2, 4, flags=1 | 4)
+    f3, d3, _ = run(emu, pcm[None], 2, 4, flags=1)
+    assert d2[0, 79] == 1.0 and np.array_equal(f2, f3) and np.array_equal(d2[:, :79], d3[:, :79], equal_nan=True)
+
+
+def test_fold_needs_both_parts(emu):
+    """Without the STFT-512 part there are no quads to ride on: the separate pass runs (detail[79] = 0), same results."""
+    x = synth.pcm_to_f32(synth.segment_pcm(1234))
+    _, d0, _ = run(emu, x[None], 2, 4, flags=1, parts=3)
+    _, d1, _ = run(emu, x[None], 2, 4, flags=1 | 4, parts=3)
+    assert d1[0, 79] == 0.0
+    assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True)
