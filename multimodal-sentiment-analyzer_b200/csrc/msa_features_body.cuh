@@ -1082,94 +1082,99 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     block_reduce<2>(env, wred, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
     const double gq = rout[0], bq = rout[1];
 
-    if (env.tid == 0) {
-      const double NaN = nan("");
-      Partials tot = *part;
-#pragma unroll 1
-      for (int rr = 1; rr < NR; ++rr) {
-        const Partials* rp = gathered + rr;
-#pragma unroll 1
-        for (int k = 0; k < kMfcc; ++k) tot.mf_sum[k] += rp->mf_sum[k];
-        tot.mf_sumsq += rp->mf_sumsq; tot.mf_abs_lo += rp->mf_abs_lo; tot.mf_abs_hi += rp->mf_abs_hi;
-        tot.p_n += rp->p_n; tot.p_sum += rp->p_sum; tot.p_sumsq += rp->p_sumsq;
-        tot.e_total += rp->e_total; tot.e_noise += rp->e_noise;
-        tot.p_max = fmaxf(tot.p_max, rp->p_max);
-        tot.mf_frames += rp->mf_frames;
-      }
-      // cold, once-per-segment code: arrays in shared memory and rolled loops keep it out of the instruction cache's way
-      float* raw = reinterpret_cast<float*>(wred);
+    // The row: warp 0, one raw feature / LayerNorm entry / output word per lane.  Every lane forms the segment-level
+    // scalars itself (uniform: the same operations in the same order a single thread would run), while the per-entry
+    // work (two fp64 divisions per MFCC coefficient, the LayerNorm entries, nan_to_num, the stores) is spread over
+    // the lanes.  (A single-thread version of this block took ~20 us per segment, 7 % of a CTA's life, during which
+    // the CTA's other warps idle at the last barrier.)
+    if (env.warp == 0) {
+      float* raw = reinterpret_cast<float*>(wred);          // raw27 staged for the LayerNorm sums
       const float* emo = P.emo8 ? P.emo8 + (size_t)seg * 8 : nullptr;
+      float q4s[S][4], dg[S][7];
+      env.lanes([&](int lane, int li) {
+        const double NaN = nan("");
+        // merge the ranks' partial moments in rank order
+        double p_n = part->p_n, p_sum = part->p_sum, p_sumsq = part->p_sumsq, e_total = part->e_total, e_noise = part->e_noise;
+        double mf_sumsq = part->mf_sumsq, mf_abs_lo = part->mf_abs_lo, mf_abs_hi = part->mf_abs_hi;
+        float p_max = part->p_max;
+        int mf_frames = part->mf_frames;
 #pragma unroll 1
-      for (int k = 0; k < 8; ++k) raw[k] = emo ? emo[k] : 0.125f;
-      // pitch: mean of the z-scored residual. mu and sigma are fp32 tensors in the reference, so the
-      // value is the rounding residue of mu; the residual itself is fp32 FFT noise (~1e-8).
-      double p_mean = 0.0, p_std = 0.0;
-      {
-        float v = 0.0f;
-        if (tot.p_n > 1.0) {
-          p_mean = tot.p_sum / tot.p_n;
-          double var = (tot.p_sumsq - tot.p_sum * p_mean) / (tot.p_n - 1.0);
+        for (int rr = 1; rr < NR; ++rr) {
+          const Partials* rp = gathered + rr;
+          mf_sumsq += rp->mf_sumsq; mf_abs_lo += rp->mf_abs_lo; mf_abs_hi += rp->mf_abs_hi;
+          p_n += rp->p_n; p_sum += rp->p_sum; p_sumsq += rp->p_sumsq;
+          e_total += rp->e_total; e_noise += rp->e_noise;
+          p_max = fmaxf(p_max, rp->p_max);
+          mf_frames += rp->mf_frames;
+        }
+        double ssum = 0.0, mf_mine = 0.0;                     // sum of all coefficient sums; the lane's own coefficient
+#pragma unroll 1
+        for (int k = 0; k < kMfcc; ++k) {
+          double t = part->mf_sum[k];
+#pragma unroll 1
+          for (int rr = 1; rr < NR; ++rr) t += gathered[rr].mf_sum[k];
+          ssum += t;
+          if (k == lane - 10) mf_mine = t;
+        }
+        float mine = 0.0f;                                    // raw[lane]
+        if (lane < 8) mine = emo ? emo[lane] : 0.125f;
+        // pitch: mean of the z-scored residual. mu and sigma are fp32 tensors in the reference, so the
+        // value is the rounding residue of mu; the residual itself is fp32 FFT noise (~1e-8).
+        double p_mean = 0.0, p_std = 0.0;
+        if (p_n > 1.0) {
+          p_mean = p_sum / p_n;
+          double var = (p_sumsq - p_sum * p_mean) / (p_n - 1.0);
           p_std = sqrt(var > 0.0 ? var : 0.0);
           const float mu32 = (float)p_mean, sd32 = (float)p_std;
-          v = (float)((tot.p_sum - tot.p_n * (double)mu32) / (tot.p_n * ((double)sd32 + 1e-6)));
+          if (lane == 8) mine = (float)((p_sum - p_n * (double)mu32) / (p_n * ((double)sd32 + 1e-6)));
         }
-        raw[8] = v;
-      }
-      // intensity: (e - mean(e)) / (std(e) + 1e-6) over ONE channel: std of one element is NaN
-      raw[9] = (P.flags & kFlagStrictNan) ? (float)NaN : 0.0f;
-      // timbre
-      double clarity = 0.0;
-      {
-        const double n = (double)tot.mf_frames * kMfcc;
-        if (tot.mf_frames > 0) {
-          double ssum = 0.0;
-#pragma unroll 1
-          for (int k = 0; k < kMfcc; ++k) ssum += tot.mf_sum[k];
+        // intensity: (e - mean(e)) / (std(e) + 1e-6) over ONE channel: std of one element is NaN
+        if (lane == 9) mine = (P.flags & kFlagStrictNan) ? (float)NaN : 0.0f;
+        // timbre
+        double clarity = 0.0;
+        if (mf_frames > 0) {
+          const double n = (double)mf_frames * kMfcc;
           const double mu = ssum / n;
-          const double var = (n > 1.0) ? (tot.mf_sumsq - ssum * mu) / (n - 1.0) : NaN;
+          const double var = (n > 1.0) ? (mf_sumsq - ssum * mu) / (n - 1.0) : NaN;
           const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : NaN));
-#pragma unroll 1
-          for (int k = 0; k < kMfcc; ++k) raw[10 + k] = (float)((tot.mf_sum[k] / tot.mf_frames - mu) / (sd + 1e-6));
-          const double hi_m = tot.mf_abs_hi / (7.0 * tot.mf_frames), lo_m = tot.mf_abs_lo / (6.0 * tot.mf_frames);
+          if (lane >= 10 && lane < 10 + kMfcc) mine = (float)((mf_mine / mf_frames - mu) / (sd + 1e-6));
+          const double hi_m = mf_abs_hi / (7.0 * mf_frames), lo_m = mf_abs_lo / (6.0 * mf_frames);
           clarity = py_clip01((double)((float)hi_m / ((float)lo_m + 1e-6f)));
-        } else {
-#pragma unroll 1
-          for (int k = 0; k < kMfcc; ++k) raw[10 + k] = 0.0f;
         }
-      }
-      // speech rate (mono): energy > 0.1 * energy in fp32
-      {
-        const float e = (float)tot.e_total;
-        raw[23] = (e > e * 0.1f) ? 1.0f : 0.0f;
-      }
-      // rhythm
-      if (nG > 0) {
-        raw[24] = (float)gmean;
-        raw[25] = (nG > 1) ? (float)sqrt(gq / (nG - 1)) : (float)NaN;
-        raw[26] = (float)((double)nG / (double)kSampleRate);
-      } else {
-        raw[24] = raw[25] = raw[26] = 0.0f;
-      }
-      // quality scalars (python floats in the reference: double arithmetic on fp32 .item() values)
-      double snr = 0.0, consistency = 0.0;
-      if (P.noise_n > 0 && (P.parts & kPartWave)) {
-        const float noise_p = (float)(tot.e_noise / (2.0 * P.noise_n));
-        const float sig_p = (float)(tot.e_total / (double)T);
-        const float snr_db = 10.0f * log10f(sig_p / (noise_p + 1e-6f));
-        snr = py_clip01((double)snr_db / 30.0);
-      }
-      if (nBk > 0) {
-        const float sd = (nBk > 1) ? (float)sqrt(bq / (nBk - 1)) : (float)NaN;
-        const double cv = (double)(sd / ((float)bmean + 1e-6f));
-        consistency = 1.0 - ((1.0 < cv) ? 1.0 : cv);   // python min(cv, 1.0): NaN stays NaN
-      }
-      if (!(P.parts & kPartMfcc)) clarity = 0.0;
-      const double quality = 0.4 * snr + 0.3 * clarity + 0.3 * consistency;
-      const float q4[4] = {(float)quality, (float)snr, (float)clarity, (float)consistency};
-
-      // AudioFeatureNormalizer: pad 27 -> 31 with zeros, LayerNorm(31) (gamma 1, beta 0, eps 1e-5, biased var)
-      float* ln = raw + 32;
-      {
+        // speech rate (mono): energy > 0.1 * energy in fp32
+        if (lane == 23) {
+          const float e = (float)e_total;
+          mine = (e > e * 0.1f) ? 1.0f : 0.0f;
+        }
+        // rhythm
+        if (nG > 0) {
+          if (lane == 24) mine = (float)gmean;
+          if (lane == 25) mine = (nG > 1) ? (float)sqrt(gq / (nG - 1)) : (float)NaN;
+          if (lane == 26) mine = (float)((double)nG / (double)kSampleRate);
+        }
+        // quality scalars (python floats in the reference: double arithmetic on fp32 .item() values)
+        double snr = 0.0, consistency = 0.0;
+        if (P.noise_n > 0 && (P.parts & kPartWave)) {
+          const float noise_p = (float)(e_noise / (2.0 * P.noise_n));
+          const float sig_p = (float)(e_total / (double)T);
+          const float snr_db = 10.0f * log10f(sig_p / (noise_p + 1e-6f));
+          snr = py_clip01((double)snr_db / 30.0);
+        }
+        if (nBk > 0) {
+          const float sd = (nBk > 1) ? (float)sqrt(bq / (nBk - 1)) : (float)NaN;
+          const double cv = (double)(sd / ((float)bmean + 1e-6f));
+          consistency = 1.0 - ((1.0 < cv) ? 1.0 : cv);   // python min(cv, 1.0): NaN stays NaN
+        }
+        if (!(P.parts & kPartMfcc)) clarity = 0.0;
+        const double quality = 0.4 * snr + 0.3 * clarity + 0.3 * consistency;
+        q4s[li][0] = (float)quality; q4s[li][1] = (float)snr; q4s[li][2] = (float)clarity; q4s[li][3] = (float)consistency;
+        dg[li][0] = (float)p_mean; dg[li][1] = (float)p_std; dg[li][2] = p_max; dg[li][3] = (float)e_total;
+        dg[li][4] = (float)e_noise; dg[li][5] = (float)mf_frames; dg[li][6] = (float)p_n;
+        if (lane < 27) raw[lane] = mine;
+      });
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+        // AudioFeatureNormalizer: pad 27 -> 31 with zeros, LayerNorm(31) (gamma 1, beta 0, eps 1e-5, biased var)
         double m = 0.0;
 #pragma unroll 1
         for (int k = 0; k < 27; ++k) m += (double)raw[k];
@@ -1179,37 +1184,32 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         for (int k = 0; k < 31; ++k) { const double d = ((k < 27) ? (double)raw[k] : 0.0) - m; v += d * d; }
         v /= 31.0;
         const double rs = 1.0 / sqrt(v + 1e-5);
-#pragma unroll 1
-        for (int k = 0; k < 31; ++k) ln[k] = (float)((((k < 27) ? (double)raw[k] : 0.0) - m) * rs);
-      }
-      // fusion input row: LN slices ++ quality, torch.nan_to_num(nan=0.0) (+-inf -> +-FLT_MAX)
-      float* out = P.feat31 + (size_t)seg * 31;
-#pragma unroll 1
-      for (int k = 0; k < 31; ++k) {
-        float v = (k < 27) ? ln[k] : q4[k - 27];
-        if (v != v) v = 0.0f;
-        else if (v > 3.4028234663852886e38f) v = 3.4028234663852886e38f;
-        else if (v < -3.4028234663852886e38f) v = -3.4028234663852886e38f;
-        out[k] = v;
-      }
-      if (P.detail) {
-        float* d = P.detail + (size_t)seg * kDetailStride;
-#pragma unroll 1
-        for (int k = 0; k < 27; ++k) d[k] = raw[k];
-#pragma unroll 1
-        for (int k = 0; k < 4; ++k) d[27 + k] = q4[k];
-        d[31] = 0.0f;
-#pragma unroll 1
-        for (int k = 0; k < 31; ++k) d[32 + k] = ln[k];
-        d[63] = 0.0f;
-        d[64] = gmax; d[65] = (float)p_mean; d[66] = (float)p_std; d[67] = tot.p_max;
-        d[68] = (float)tot.e_total; d[69] = (float)tot.e_noise; d[70] = (float)tot.mf_frames; d[71] = (float)nG;
-        d[72] = (float)tot.p_n; d[73] = (float)nBk; d[74] = (float)nA;
-        d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
-#pragma unroll 1
-        for (int k = 79; k < kDetailStride; ++k) d[k] = 0.0f;
-        if constexpr (FOLD) d[79] = 1.0f;                  // which variant produced the row
-      }
+        const float mine = (lane < 27) ? raw[lane] : 0.0f;
+        const float lnv = (float)(((double)mine - m) * rs);
+        // fusion input row: LN slices ++ quality, torch.nan_to_num(nan=0.0) (+-inf -> +-FLT_MAX)
+        if (lane < 31) {
+          float o = (lane < 27) ? lnv : q4s[li][lane - 27];
+          if (o != o) o = 0.0f;
+          else if (o > 3.4028234663852886e38f) o = 3.4028234663852886e38f;
+          else if (o < -3.4028234663852886e38f) o = -3.4028234663852886e38f;
+          P.feat31[(size_t)seg * 31 + lane] = o;
+        }
+        if (P.detail) {
+          float* d = P.detail + (size_t)seg * kDetailStride;
+          if (lane < 27) d[lane] = mine;
+          if (lane < 4) d[27 + lane] = q4s[li][lane];
+          if (lane < 31) d[32 + lane] = lnv;
+          if (lane == 31) { d[31] = 0.0f; d[63] = 0.0f; }
+          if (lane == 0) {
+            d[64] = gmax; d[65] = dg[li][0]; d[66] = dg[li][1]; d[67] = dg[li][2];
+            d[68] = dg[li][3]; d[69] = dg[li][4]; d[70] = dg[li][5]; d[71] = (float)nG;
+            d[72] = dg[li][6]; d[73] = (float)nBk; d[74] = (float)nA;
+            d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
+            d[79] = FOLD ? 1.0f : 0.0f;                      // which variant produced the row
+          }
+          if (lane < kDetailStride - 80) d[80 + lane] = 0.0f;
+        }
+      });
     }
   }
   env.csync();                                            // #3: nobody exits while rank 0 still reads its smem

@@ -1,0 +1,143 @@
+// A/B check of several BUILDS of libmsa_b200.so (the first is the baseline), straight through the C ABI (dlopen; no
+// Python, no torch: starts in a second on a fresh box).  For every library: the 31-float rows and the detail rows
+// of a set of (B, T, cluster, dtype, flags) cases are compared bit for bit with the baseline's, then all libraries
+// are timed in turn (A B C A B C) on BASELINE configs[1] (1024 x 5 s) with CUDA events: on all-voiced segments (the
+// bench's kind of input) and with 0.8 s of digital silence in every 7th segment (top_db overflow path).
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/ab_check scripts/ab_check.cu -ldl
+//   ./scripts/ab_check base.so new.so [more.so ...] > gpurun_out/ab_check.json
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("{\"error\": \"%s at line %d\"}\n", cudaGetErrorString(e_), __LINE__); return 2; } } while (0)
+
+typedef int (*feat_f32_t)(const float*, int, int, const float*, float*, float*, float*, int, int, int, void*);
+typedef int (*feat_s16_t)(const int16_t*, int, int, const float*, float*, float*, float*, int, int, int, void*);
+
+__device__ unsigned hash_u32(unsigned x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
+
+// voiced-speech-like segments: 5 harmonics under a syllabic envelope plus noise, quantised to int16
+__global__ void synth_kernel(int16_t* pcm, float* wav, float* emo, int B, int T, int silence) {
+  const size_t n = (size_t)B * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int seg = (int)(i / T), t = (int)(i % T);
+    const float f0 = 80.0f + 220.0f * (hash_u32(seg * 2 + 1) * (1.0f / 4294967296.0f));
+    const float r = 2.0f + 4.0f * (hash_u32(seg * 2 + 2) * (1.0f / 4294967296.0f));
+    const float ts = t / 16000.0f;
+    float v = 0.0f;
+    for (int k = 1; k <= 5; ++k) v += (0.3f / k) * __sinf(6.2831853f * f0 * k * ts);
+    v *= 0.5f + 0.5f * __sinf(6.2831853f * r * ts);
+    const unsigned h = hash_u32((unsigned)i * 2654435761u + 12345u);
+    v += 0.02f * ((float)(h & 0xffff) + (float)(h >> 16) - 65535.0f) * (1.0f / 26754.0f);
+    if (silence && seg % 7 == 3 && t > T / 3 && t < T / 2) v = 0.0f;
+    v = fminf(fmaxf(v, -1.0f), 1.0f);
+    const int q = __float2int_rn(v * 32767.0f);
+    pcm[i] = (int16_t)q;
+    wav[i] = (float)q * (1.0f / 32768.0f);
+    if (t < 8) emo[seg * 8 + t] = (0.5f + (hash_u32(seg * 8 + t + 99) & 255)) * (1.0f / 1024.0f);
+  }
+}
+
+int main(int argc, char** argv) {
+  const int nlib = argc - 1;
+  if (nlib < 2 || nlib > 6) { printf("{\"error\": \"usage: ab_check base.so new.so [...]\"}\n"); return 2; }
+  feat_f32_t f32[6]; feat_s16_t s16[6];
+  for (int l = 0; l < nlib; ++l) {
+    void* h = dlopen(argv[1 + l], RTLD_NOW | RTLD_LOCAL);
+    if (!h) { printf("{\"error\": \"dlopen: %s\"}\n", dlerror()); return 2; }
+    f32[l] = (feat_f32_t)dlsym(h, "msa_features_f32");
+    s16[l] = (feat_s16_t)dlsym(h, "msa_features_s16");
+    if (!f32[l] || !s16[l]) { printf("{\"error\": \"missing symbols\"}\n"); return 2; }
+  }
+  const int Bmax = 1024, Tmax = 80640;
+  int16_t* pcm; float *wav, *emo, *feat, *det;
+  CK(cudaMalloc(&pcm, (size_t)Bmax * Tmax * 2));
+  CK(cudaMalloc(&wav, (size_t)Bmax * Tmax * 4));
+  CK(cudaMalloc(&emo, Bmax * 8 * 4));
+  CK(cudaMalloc(&feat, Bmax * 31 * 4));
+  CK(cudaMalloc(&det, Bmax * 96 * 4));
+  std::vector<float> hf[2], hd[2];
+  for (int v = 0; v < 2; ++v) { hf[v].resize(Bmax * 31); hd[v].resize(Bmax * 96); }
+
+  printf("{\"what\": \"feature kernel builds vs the first one, bitwise (rows and the detail columns except [79])\", \"libs\": [");
+  for (int l = 0; l < nlib; ++l) printf("%s\"%s\"", l ? ", " : "", argv[1 + l]);
+  printf("], \"cases\": [");
+  struct Case { int B, T, c, is16, flags, parts, emo; };
+  const Case cases[] = {{1024, 80000, 0, 0, 1, 7, 0}, {1024, 80000, 0, 1, 1, 7, 1}, {64, 80000, 2, 0, 0, 7, 1}, {16, 80000, 4, 0, 1, 7, 0}, {4, 80000, 8, 0, 1, 7, 1},
+                        {1, 80000, 0, 0, 1, 7, 0}, {64, 12345, 1, 0, 1, 7, 0}, {64, 80129, 1, 0, 1, 7, 0}, {64, 80127, 2, 1, 0, 7, 1}, {64, 30001, 1, 0, 1, 3, 0},
+                        {64, 513, 1, 0, 1, 7, 0}, {64, 1700, 1, 1, 1, 5, 0}, {64, 257, 1, 0, 1, 7, 0}, {64, 100, 1, 0, 1, 7, 1}, {64, 399, 1, 0, 1, 7, 0},
+                        {256, 80000, 0, 0, 5, 7, 0}, {64, 160000, 0, 1, 1, 7, 0}};
+  int bad_total = 0;
+  bool first = true;
+  for (const Case& cs : cases) {
+    synth_kernel<<<592, 256>>>(pcm, wav, emo, cs.B, cs.T, 1);
+    CK(cudaGetLastError());
+    for (int l = 0; l < nlib; ++l) {
+      const int v = l ? 1 : 0;
+      CK(cudaMemset(feat, 0xFF, Bmax * 31 * 4));
+      CK(cudaMemset(det, 0xFF, Bmax * 96 * 4));
+      const int rc = cs.is16 ? s16[l](pcm, cs.B, cs.T, cs.emo ? emo : nullptr, feat, det, nullptr, cs.flags, cs.parts, cs.c, nullptr)
+                             : f32[l](wav, cs.B, cs.T, cs.emo ? emo : nullptr, feat, det, nullptr, cs.flags, cs.parts, cs.c, nullptr);
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(hf[v].data(), feat, cs.B * 31 * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hd[v].data(), det, cs.B * 96 * 4, cudaMemcpyDeviceToHost));
+      if (l == 0) {
+        if (rc != 0) ++bad_total;
+        printf("%s{\"B\": %d, \"T\": %d, \"cluster\": %d, \"s16\": %d, \"flags\": %d, \"parts\": %d, \"emo\": %d, \"rc\": %d, \"quality_row0\": %.7g, \"rows_differing\": [",
+               first ? "" : ", ", cs.B, cs.T, cs.c, cs.is16, cs.flags, cs.parts, cs.emo, rc, hf[0][27]);
+        first = false;
+        continue;
+      }
+      int bad_rows = 0;
+      for (int b = 0; b < cs.B; ++b)
+        bad_rows += memcmp(&hf[0][b * 31], &hf[1][b * 31], 31 * 4) != 0 || memcmp(&hd[0][b * 96], &hd[1][b * 96], 79 * 4) != 0 ||
+                    memcmp(&hd[0][b * 96 + 80], &hd[1][b * 96 + 80], 16 * 4) != 0;   // [79] names the variant that made the row
+      bad_total += bad_rows + (rc != 0);
+      printf("%s%d", l > 1 ? ", " : "", bad_rows);
+    }
+    printf("]}");
+  }
+  printf("], \"rows_differing_total\": %d, \"timing_ms_per_1024_segments\": {", bad_total);
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  first = true;
+  for (int silence = 0; silence < 2; ++silence) {
+    synth_kernel<<<592, 256>>>(pcm, wav, emo, 1024, 80000, silence);
+    CK(cudaDeviceSynchronize());
+    for (int is16 = 0; is16 < 2; ++is16)
+      for (int rep = 0; rep < 2; ++rep)          // A B C A B C: drift shows up as a difference between the repeats
+        for (int l = 0; l < nlib; ++l) {
+          for (int i = 0; i < 3; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr)
+                                           : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+          CK(cudaDeviceSynchronize());
+          CK(cudaEventRecord(e0));
+          for (int i = 0; i < 20; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr)
+                                            : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+          CK(cudaEventRecord(e1));
+          CK(cudaEventSynchronize(e1));
+          float ms = 0.0f;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          printf("%s\"%s_%s_lib%d_%d\": %.4f", first ? "" : ", ", silence ? "silence" : "voiced", is16 ? "s16" : "f32", l, rep, ms / 20.0f);
+          first = false;
+        }
+  }
+  // streaming shape: one segment over a cluster of 8 CTAs (auto), 200 launches
+  for (int l = 0; l < nlib; ++l) {
+    for (int i = 0; i < 20; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 200; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.0f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    printf(", \"one_segment_us_lib%d\": %.2f", l, 1000.0f * ms / 200.0f);
+  }
+  printf("}}\n");
+  return bad_total ? 1 : 0;
+}
