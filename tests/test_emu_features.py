@@ -204,3 +204,22 @@ def test_fold_needs_both_parts(emu):
     _, d1, _ = run(emu, x[None], 2, 4, flags=1 | 4, parts=3)
     assert d1[0, 79] == 0.0
     assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True)
+
+
+def test_fold_sweep_of_lengths_and_shapes(emu):
+    """Every length around the atom (80), entry (4), quad (512) and frame boundaries, random cluster shapes:
+    the folded statistics give the default kernel's bits."""
+    rng = np.random.default_rng(7)
+    lengths = list(range(257, 290)) + [320, 339, 340, 399, 400, 401, 511, 512, 575, 576, 767, 768, 769, 1279, 1280, 1281, 1599, 1600,
+                                       2047, 2048, 5119, 5120, 5121] + [int(t) for t in rng.integers(300, 9000, 12)]
+    for n, T in enumerate(lengths):
+        x = (rng.standard_normal(T) * 3000).astype(np.int16)
+        if n % 5 == 0:
+            x[T // 3: T // 2] = 0
+        nranks, nwarps = int(rng.choice([1, 2, 4, 8])), int(rng.integers(1, 9))
+        f0, d0, g0 = run(emu, x[None], nranks, nwarps, flags=1)
+        f1, d1, g1 = run(emu, x[None], nranks, nwarps, flags=1 | 4)
+        assert d1[0, 79] == 1.0
+        assert np.array_equal(f0, f1), (T, nranks, nwarps)
+        assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True), (T, nranks, nwarps)
+        assert np.array_equal(g0, g1), (T, nranks, nwarps)
