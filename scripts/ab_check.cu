@@ -2,14 +2,20 @@
 // Python, no torch: starts in a second on a fresh box).  For every library: the 31-float rows and the detail rows
 // of a set of (B, T, cluster, dtype, flags) cases are compared bit for bit with the baseline's, then all libraries
 // are timed in turn (A B C A B C) on BASELINE configs[1] (1024 x 5 s) with CUDA events: on all-voiced segments (the
-// bench's kind of input) and with 0.8 s of digital silence in every 7th segment (top_db overflow path).
+// bench's kind of input) and with 0.8 s of digital silence in every 7th segment (top_db overflow path).  A second part does
+// the same for the 3-modal fusion forward (same random state_dict packed by every library, batches 1 .. 65,536: max
+// |logit difference| and argmax mismatches against the baseline, microseconds per forward).  The feature part ran on
+// B200 in round 1 (profiles/r1_v11_ab_*.json); the fusion part was written after the round's GPU budget was spent
+// and has only been compiled.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/ab_check scripts/ab_check.cu -ldl
 //   ./scripts/ab_check base.so new.so [more.so ...] > gpurun_out/ab_check.json
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -17,6 +23,14 @@
 
 typedef int (*feat_f32_t)(const float*, int, int, const float*, float*, float*, float*, int, int, int, void*);
 typedef int (*feat_s16_t)(const int16_t*, int, int, const float*, float*, float*, float*, int, int, int, void*);
+
+typedef int (*fus_num_t)(void);
+typedef size_t (*fus_numel_t)(int);
+typedef size_t (*fus_bytes_t)(void);
+typedef size_t (*fus_ws_t)(int);
+typedef int (*fus_pack_t)(const float* const*, void*, void*);
+typedef int (*fus_fwd_t)(const float*, const float*, const float*, int, const void*, void*, size_t, float*, int32_t*, void*);
+typedef const char* (*fus_name_t)(int);
 
 __device__ unsigned hash_u32(unsigned x) { x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16; return x; }
 
@@ -138,6 +152,101 @@ int main(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ms, e0, e1));
     printf(", \"one_segment_us_lib%d\": %.2f", l, 1000.0f * ms / 200.0f);
   }
-  printf("}}\n");
+  printf("}");
+
+  // ---- fusion forward (AdvancedFusionModel, 3-modal): every library packs the same random state_dict and runs the same
+  // rows; logits are compared with the baseline's (max |diff|, argmax mismatches: a variant that changes the summation
+  // order is not bit-identical) and the forward is timed per batch size.  MSA_AB_FUSION=0 skips this part.
+  const char* fe = getenv("MSA_AB_FUSION");
+  if (!(fe && fe[0] == '0')) {
+    printf(", \"fusion\": [");
+    const int batches[] = {1, 8, 64, 1024, 4096, 65536};
+    const int Bf = 65536;
+    float *face, *audio, *text, *logits;
+    int32_t* amax;
+    CK(cudaMalloc(&face, (size_t)Bf * 27 * 4)); CK(cudaMalloc(&audio, (size_t)Bf * 31 * 4)); CK(cudaMalloc(&text, (size_t)Bf * 783 * 4));
+    CK(cudaMalloc(&logits, (size_t)Bf * 7 * 4)); CK(cudaMalloc(&amax, (size_t)Bf * 4));
+    {
+      std::vector<float> h((size_t)Bf * 783);
+      unsigned st = 12345u;
+      auto rnd = [&]() { st = st * 1664525u + 1013904223u; return ((st >> 8) & 0xffff) * (1.0f / 65536.0f) - 0.5f; };
+      for (size_t i = 0; i < (size_t)Bf * 783; ++i) h[i] = 2.0f * rnd();
+      CK(cudaMemcpy(text, h.data(), (size_t)Bf * 783 * 4, cudaMemcpyHostToDevice));
+      for (size_t i = 0; i < (size_t)Bf * 31; ++i) h[i] = 2.0f * rnd();
+      CK(cudaMemcpy(audio, h.data(), (size_t)Bf * 31 * 4, cudaMemcpyHostToDevice));
+      for (size_t i = 0; i < (size_t)Bf * 27; ++i) h[i] = ((i % 27) < 23) ? 2.0f * rnd() : 300.0f * (rnd() + 0.5f);   // raw pixel boxes in the last 4
+      CK(cudaMemcpy(face, h.data(), (size_t)Bf * 27 * 4, cudaMemcpyHostToDevice));
+    }
+    std::vector<float> ref((size_t)Bf * 7), cur((size_t)Bf * 7);
+    std::vector<int32_t> refa(Bf), cura(Bf);
+    std::vector<void*> packed(nlib), wsp(nlib);
+    std::vector<size_t> wsb(nlib);
+    std::vector<fus_fwd_t> fwd(nlib);
+    for (int l = 0; l < nlib; ++l) {
+      void* h = dlopen(argv[1 + l], RTLD_NOW | RTLD_LOCAL);
+      fus_num_t num = (fus_num_t)dlsym(h, "msa_fusion_num_tensors");
+      fus_numel_t numel = (fus_numel_t)dlsym(h, "msa_fusion_tensor_numel");
+      fus_name_t tname = (fus_name_t)dlsym(h, "msa_fusion_tensor_name");
+      fus_bytes_t pbytes = (fus_bytes_t)dlsym(h, "msa_fusion_packed_bytes");
+      fus_ws_t wbytes = (fus_ws_t)dlsym(h, "msa_fusion_workspace_bytes");
+      fus_pack_t pack = (fus_pack_t)dlsym(h, "msa_fusion_pack");
+      fwd[l] = (fus_fwd_t)dlsym(h, "msa_fusion_forward");
+      if (!num || !numel || !tname || !pbytes || !wbytes || !pack || !fwd[l]) { printf("{\"error\": \"fusion symbols\"}]}\n"); return 2; }
+      const int nt = num();
+      std::vector<std::vector<float>> tens(nt);
+      std::vector<const float*> ptr(nt);
+      unsigned st = 777u;                                   // the same values for every library
+      auto rnd = [&]() { st = st * 1664525u + 1013904223u; return ((st >> 8) & 0xffff) * (1.0f / 65536.0f) - 0.5f; };
+      for (int i = 0; i < nt; ++i) {
+        const size_t n = numel(i);
+        const char* nm = tname(i);
+        const bool is_w = strstr(nm, "weight") != nullptr, is_norm = strstr(nm, "norm") != nullptr;
+        tens[i].resize(n);
+        // Linear weights ~ U(-0.05, 0.05), LayerNorm weights 1 +- 0.1, biases / betas +- 0.1, anything else (modality weights) +- 0.5
+        for (size_t k = 0; k < n; ++k) tens[i][k] = (is_w && !is_norm && n > 2048) ? 0.1f * rnd() : ((is_w && n > 3) ? 1.0f + 0.2f * rnd() : (n > 3 ? 0.2f * rnd() : rnd()));
+        ptr[i] = tens[i].data();
+      }
+      CK(cudaMalloc(&packed[l], pbytes()));
+      const int rc = pack(ptr.data(), packed[l], nullptr);
+      if (rc != 0) { printf("{\"error\": \"pack rc %d\"}]}\n", rc); return 2; }
+      wsb[l] = wbytes(Bf);
+      CK(cudaMalloc(&wsp[l], wsb[l]));
+      CK(cudaDeviceSynchronize());
+    }
+    first = true;
+    for (int B : batches) {
+      printf("%s{\"B\": %d", first ? "" : ", ", B);
+      first = false;
+      for (int l = 0; l < nlib; ++l) {
+        CK(cudaMemset(logits, 0xFF, (size_t)B * 7 * 4));
+        int rc = fwd[l](face, audio, text, B, packed[l], wsp[l], wsb[l], logits, amax, nullptr);
+        CK(cudaDeviceSynchronize());
+        std::vector<float>& out = l ? cur : ref;
+        std::vector<int32_t>& oa = l ? cura : refa;
+        CK(cudaMemcpy(out.data(), logits, (size_t)B * 7 * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(oa.data(), amax, (size_t)B * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < 3; ++i) fwd[l](face, audio, text, B, packed[l], wsp[l], wsb[l], logits, amax, nullptr);
+        CK(cudaDeviceSynchronize());
+        const int reps = B >= 4096 ? 10 : 50;
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < reps; ++i) fwd[l](face, audio, text, B, packed[l], wsp[l], wsb[l], logits, amax, nullptr);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (l == 0) {
+          printf(", \"rc0\": %d, \"logit0\": %.6g, \"us_lib0\": %.2f", rc, ref[0], 1000.0f * ms / reps);
+        } else {
+          double md = 0.0; int mism = 0;
+          for (size_t i = 0; i < (size_t)B * 7; ++i) { const double d = fabs((double)cur[i] - (double)ref[i]); if (!(d <= md)) md = d; }
+          for (int b = 0; b < B; ++b) mism += cura[b] != refa[b];
+          printf(", \"rc%d\": %d, \"max_abs_diff_lib%d\": %.3g, \"argmax_mismatch_lib%d\": %d, \"us_lib%d\": %.2f", l, rc, l, md, l, mism, l, 1000.0f * ms / reps);
+        }
+      }
+      printf("}");
+    }
+    printf("]");
+  }
+  printf("}\n");
   return bad_total ? 1 : 0;
 }
