@@ -23,14 +23,16 @@
 //
 //   "pitch"  B is followed at once, in the same registers, by the inverse radix-32 (the vocoder at
 //            rate 1.0 returns its input), then the inverse pass A, the synthesis window and the
-//            overlap-add of the quad's 4 frames in registers.  The 3 hop-blocks that overlap the
-//            next quad travel through a 1.5 KB shared-memory tile per warp.
+//            overlap-add of the quad's 4 frames in registers.  Every warp owns a contiguous run of
+//            quads and carries the 3 hop-blocks that overlap the next quad in registers.
 //   MFCC     power of both packed frames from Z_k and Z_(N-k), sparse mel (each lane owns 4 filters),
 //            dB, and the lane's share of the DCT; a 52 x 32 shared-memory transpose sums the shares.
 //            top_db needs the segment maximum, which is only known after the last frame: the DCT is
-//            linear, the four EMPTY mel filters sit at max(-100, max-80) dB for every frame and enter
-//            as one constant vector afterwards, and a live filter below max-80 dB (digital silence
-//            inside a loud segment) triggers a second, clamped MFCC pass.
+//            linear, so the four EMPTY mel filters (max(-100, max-80) dB in every frame) enter as one
+//            constant vector afterwards, and the few live values that can fall below max-80 dB (known
+//            in advance from an upper bound of the maximum) go on per-warp candidate lists and are
+//            patched in as the DCT of their clamp deltas; a list that overflows redoes its quads
+//            (or re-reads their dB values from an optional scratch table) with the deltas inline.
 //
 // Whole-segment dependencies (top_db maximum, z-score moments, frame-energy statistics) are
 // exchanged through distributed shared memory; rank 0 assembles the 31-float row.
