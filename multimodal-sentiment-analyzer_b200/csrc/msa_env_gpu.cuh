@@ -35,6 +35,9 @@ struct GpuEnv {
   __device__ __forceinline__ float ld_last(const float* p) { return __ldcs(p); }
   __device__ __forceinline__ float ld_last(const int16_t* p) { return s16_to_f32((int)__ldcs(p)); }
 
+  // request the 128-byte line at p into L2 (no register, no wait)
+  __device__ __forceinline__ void prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
   // samples idx .. idx+3 of a segment of T samples (0 beyond the end), one vector load when aligned
   __device__ __forceinline__ void ld4(const float* x, int idx, int T, float* v) {
     const float* p = x + idx;

@@ -405,6 +405,18 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         const int f0 = 4 * quad;
         const int s0 = kHopP * f0 - kNfftP / 2;                  // first sample of frame f0
         const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
+#ifdef MSA_VAR_PREFETCH
+        // experiment (scripts/build_variant.sh, not in the default build): the 512 samples the NEXT quad of this warp
+        // adds (t = s0 + 896 .. s0 + 1407) are requested now, one 128-byte line per lane, so that their first touch
+        // (from HBM with FOLD, where no statistics pass has read the segment before) overlaps this quad's arithmetic
+        if (quad + 1 < wq_end && s0 + 896 + 512 <= T) {
+          env.lanes([&](int lane, int li) {
+            (void)li;
+            constexpr int kPerLine = 128 / (int)sizeof(InT);
+            if (lane * kPerLine < 512) env.prefetch(x + s0 + 896 + lane * kPerLine);
+          });
+        }
+#endif
         // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples.  The quad spans
         // 7 hop-blocks = 28 samples per lane, loaded once and shared by both FFTs (frames overlap by 3/4)
         env.lanes([&](int lane, int li) {

@@ -49,6 +49,7 @@ struct CpuEnv {
   float log2(float v) { return std::log2(v); }
   float ld(const float* p) { return *p; }
   float ld(const int16_t* p) { return (float)*p * (1.0f / 32768.0f); }
+  void prefetch(const void*) {}
   float ld_last(const float* p) { return ld(p); }
   float ld_last(const int16_t* p) { return ld(p); }
   template <class InT> void ld4(const InT* x, int idx, int T, float* v) {
