@@ -8,7 +8,7 @@
 // B200 in round 1 (profiles/r1_v11_ab_*.json); the fusion part was written after the round's GPU budget was spent
 // and has only been compiled.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/ab_check scripts/ab_check.cu -ldl
-//   ./scripts/ab_check base.so new.so [more.so ...] > gpurun_out/ab_check.json
+//   ./scripts/ab_check base.so new.so [more.so ...] > gpurun_out/ab_check.json     ("lib.so@5": time that library with feature flags 5 = FOLD)
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -60,7 +60,11 @@ int main(int argc, char** argv) {
   const int nlib = argc - 1;
   if (nlib < 2 || nlib > 6) { printf("{\"error\": \"usage: ab_check base.so new.so [...]\"}\n"); return 2; }
   feat_f32_t f32[6]; feat_s16_t s16[6];
+  int tflags[6];                                        // feature flags used in the TIMED launches: "lib.so@5" = strict NaN + FOLD
   for (int l = 0; l < nlib; ++l) {
+    tflags[l] = 1;
+    char* at = strrchr(argv[1 + l], '@');
+    if (at) { tflags[l] = atoi(at + 1); *at = 0; }
     void* h = dlopen(argv[1 + l], RTLD_NOW | RTLD_LOCAL);
     if (!h) { printf("{\"error\": \"dlopen: %s\"}\n", dlerror()); return 2; }
     f32[l] = (feat_f32_t)dlsym(h, "msa_features_f32");
@@ -126,12 +130,12 @@ int main(int argc, char** argv) {
     for (int is16 = 0; is16 < 2; ++is16)
       for (int rep = 0; rep < 2; ++rep)          // A B C A B C: drift shows up as a difference between the repeats
         for (int l = 0; l < nlib; ++l) {
-          for (int i = 0; i < 3; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr)
-                                           : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+          for (int i = 0; i < 3; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr)
+                                           : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr);
           CK(cudaDeviceSynchronize());
           CK(cudaEventRecord(e0));
-          for (int i = 0; i < 20; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr)
-                                            : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+          for (int i = 0; i < 20; ++i) is16 ? s16[l](pcm, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr)
+                                            : f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr);
           CK(cudaEventRecord(e1));
           CK(cudaEventSynchronize(e1));
           float ms = 0.0f;
@@ -142,10 +146,10 @@ int main(int argc, char** argv) {
   }
   // streaming shape: one segment over a cluster of 8 CTAs (auto), 200 launches
   for (int l = 0; l < nlib; ++l) {
-    for (int i = 0; i < 20; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+    for (int i = 0; i < 20; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr);
     CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < 200; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, 1, 7, 0, nullptr);
+    for (int i = 0; i < 200; ++i) s16[l](pcm, 1, 80000, nullptr, feat, nullptr, nullptr, tflags[l], 7, 0, nullptr);
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0.0f;
