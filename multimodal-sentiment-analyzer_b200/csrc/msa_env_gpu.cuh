@@ -4,6 +4,7 @@
 #pragma once
 #include <cooperative_groups.h>
 #include <cstdint>
+#include "msa_half.h"
 #include "msa_features_body.cuh"
 
 namespace msa {
@@ -77,6 +78,81 @@ struct GpuEnv {
       ld4(x, idx, T, v);
       ld4(x, idx + 4, T, v + 4);
     }
+  }
+
+  // ---- tensor-core STFT-512 round trip (msa_pitch_tc.cuh): fp16 pairs in 32-bit registers
+  __device__ __forceinline__ u32 ldu(const u32* p) { return __ldg(p); }
+  __device__ __forceinline__ float cospi(float v) { return cospif(v); }
+  // 16 consecutive samples idx .. idx + 15, all inside the segment
+  __device__ __forceinline__ void ld16(const float* x, int idx, float* v) {
+    const float* p = x + idx;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldg(p + i);
+    }
+  }
+  __device__ __forceinline__ void ld16(const int16_t* x, int idx, float* v) {
+    const int16_t* p = x + idx;
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(p) + i);
+        const int w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          v[8 * i + 2 * k] = s16_to_f32((int)(short)(w[k] & 0xffff));
+          v[8 * i + 2 * k + 1] = s16_to_f32(w[k] >> 16);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = s16_to_f32((int)__ldg(p + i));
+    }
+  }
+  // 16 fp16 values (8 pairs) to 32-byte aligned shared memory
+  __device__ __forceinline__ void st16(uint16_t* dst, const u32* w) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+  __device__ __forceinline__ u32 lds1(const u32* p) { return *p; }
+  __device__ __forceinline__ void lds2(u32* d, const u32* p) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    d[0] = v.x; d[1] = v.y;
+  }
+  __device__ __forceinline__ void lds4(u32* d, const u32* p) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+  // D (16 x 8, fp16) = A (16 x 16) B (16 x 8) [+ D]: the getters return the lane's registers
+  template <class D, class A, class B> __device__ __forceinline__ void mma(D dg, A ag, B bg, bool accumulate) {
+    u32* d = dg(0);
+    const u32* a = ag(0);
+    const u32* b = bg(0);
+    const u32 c0 = accumulate ? d[0] : 0u, c1 = accumulate ? d[1] : 0u;
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%9};"
+                 : "=r"(d[0]), "=r"(d[1])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(c0), "r"(c1));
+  }
+  // four transposed 8 x 8 fp16 tiles: lane l supplies the address of row l % 8 of tile l / 8 (8 contiguous values)
+  template <class R, class P> __device__ __forceinline__ void ldsm4t(R rg, P pg) {
+    u32* r = rg(0);
+    const u32 addr = (u32)__cvta_generic_to_shared(pg(0));
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+  }
+  // transpose one 8 x 8 fp16 tile held across the warp (lane g, t: row g, columns 2 t, 2 t + 1), in place
+  template <class D> __device__ __forceinline__ void movmt(D dg) {
+    u32* d = dg(0);
+    u32 o;
+    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(o) : "r"(d[0]));
+    d[0] = o;
   }
 
   // block-wide copy of a 16-byte aligned table into shared memory

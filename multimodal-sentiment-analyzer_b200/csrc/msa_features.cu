@@ -9,8 +9,8 @@
 
 namespace msa {
 
-template <class InT, int THREADS, bool FOLD = false>
-__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) features_kernel(const FeatParams P) {
+template <class InT>
+__global__ void __launch_bounds__(kFeatThreads, 2) features_kernel(const FeatParams P) {
   extern __shared__ __align__(128) unsigned char smem[];
   cg::cluster_group cluster = cg::this_cluster();
   GpuEnv env;
@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1) features_kern
   env.rank = (int)cluster.block_rank();
   env.nranks = (int)cluster.num_blocks();
   env.cluster_id = blockIdx.x / env.nranks;
-  features_cta<GpuEnv, InT, FOLD>(env, P, smem);
+  features_cta<GpuEnv, InT>(env, P, smem);
 }
 
 static std::mutex g_tab_mutex;
@@ -48,15 +48,7 @@ static int get_tables(const FeatureTables** out) {
   return MSA_OK;
 }
 
-// Tuning knob (read once): MSA_FEAT_THREADS = 256 | 512 threads per CTA.
-static int env_int(const char* name, int dflt) {
-  const char* e = std::getenv(name);
-  return (e && *e) ? std::atoi(e) : dflt;
-}
-int feat_threads() {
-  static const int t = (env_int("MSA_FEAT_THREADS", kFeatThreads) == 256) ? 256 : 512;
-  return t;
-}
+int feat_threads() { return kFeatThreads; }
 
 // Smallest cluster whose per-CTA shared-memory layout lets two CTAs share an SM, else the smallest that
 // fits at all (the per-segment MFCC tile and the energy atoms are split over the ranks; everything else
@@ -123,21 +115,13 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   // optional scratch table of mel dB values (see FeatParams::dbscratch); too small or absent: quads are recomputed
   P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
-  static const int no_lockstep = env_int("MSA_FEAT_LOCKSTEP", 1) == 0 ? kFlagNoLockstep : 0;   // tuning knob (read once)
-  // opt-in (flag bit 4 or MSA_FEAT_FOLD=1, read once): the wave statistics ride on the STFT-512 quads instead of
-  // making their own pass over the segment (features_cta<.., FOLD>; bit-identical results).  Needs both parts and the
-  // 256-thread CTA; otherwise the separate pass runs.
-  static const int fold_env = env_int("MSA_FEAT_FOLD", 0) != 0 ? kFlagFoldWave : 0;
-  P.flags = flags | no_lockstep | fold_env;
+  P.flags = flags;
   P.parts = parts;
   const int threads = feat_threads();
-  bool fold = (P.flags & kFlagFoldWave) && (parts & kPartWave) && (parts & kPartPitch) && threads == 256;
-  if (fold && feat_layout(T, c, threads / 32, true).total > kMaxSmem) fold = false;
-  const FeatLayout lay = feat_layout(T, c, threads / 32, fold);
+  const FeatLayout lay = feat_layout(T, c, threads / 32);
   if (lay.total > kMaxSmem) return MSA_ERR_UNSUPPORTED_LENGTH;
 
-  auto kern = fold ? features_kernel<InT, 256, true>
-                   : ((threads == 256) ? features_kernel<InT, 256> : features_kernel<InT, 512>);
+  auto kern = features_kernel<InT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total);
   if (e != cudaSuccess) return (int)e;
   cudaLaunchConfig_t cfg{};

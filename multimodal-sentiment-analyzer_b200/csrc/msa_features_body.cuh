@@ -46,6 +46,7 @@
 #include "msa_fft.cuh"
 #include "msa_hd.h"
 #include "msa_tables.hpp"
+#include "msa_pitch_tc.cuh"
 
 namespace msa {
 
@@ -62,7 +63,7 @@ constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (th
 constexpr int kClampCap = (kWarpBufBytes - kShareBytes) / 8;
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
-enum : int { kFlagStrictNan = 1, kFlagNoLockstep = 2, kFlagFoldWave = 4 };   // kFlagFoldWave: see features_cta<.., FOLD>
+enum : int { kFlagStrictNan = 1 };
 
 struct FeatParams {
   const void* wav;       // [B, T] fp32 or int16
@@ -115,41 +116,18 @@ int pitch_quads(int T) {
   const int nBl = (T - 1 + kNfftP / 2) / kHopP + 1;
   return ((nFp > nBl ? nFp : nBl) + 3) / 4;
 }
-inline
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-int fold_quads_per_rank(int T, int nranks) { return (pitch_quads(T) + nranks - 1) / nranks; }
-// FOLD: energy atom a (samples 80 a .. 80 a + 79, entries 20 a .. 20 a + 19; the ragged last one ends with the segment)
-// is finished by the quad whose 512 own samples (t = 512 q - 256 ..) hold its last entry
-inline
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-int fold_last_entry(int a, int T) { const int e = 20 * a + 19, m = (T - 1) >> 2; return e < m ? e : m; }
-inline
-#ifdef __CUDACC__
-__host__ __device__
-#endif
-int fold_first_atom_of_quad(int q0) { return q0 <= 0 ? 0 : (128 * q0 - 83 + 19) / 20; }   // smallest a with (20 a + 83) >> 7 >= q0
-
 // identical on host (launch configuration) and device (carve-up)
 inline
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-FeatLayout feat_layout(int T, int nranks, int nwarps, bool fold = false) {
+FeatLayout feat_layout(int T, int nranks, int nwarps) {
   FeatLayout l;
   int off = 0;
   auto take = [&](int bytes) { int o = off; off += (bytes + 15) & ~15; return o; };
   const int nFm = T / kHopM + 1;
   l.mfl_frames = 4 * ((((nFm + 3) / 4) + nranks - 1) / nranks);
   l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
-  if (fold) {
-    // FOLD: a rank holds the atoms that END in its STFT-512 quads (128 entries of 4 samples per quad, 20 per atom)
-    const int cap = (128 * fold_quads_per_rank(T, nranks)) / 20 + 2;
-    if (l.atoms_cap < cap) l.atoms_cap = cap;
-  }
   int buf = nwarps * kWarpBufBytes;
   // rank 0 gathers all energy atoms and every rank's Partials there at the end
   const int gather = (((T / kAtom + 8) * 4 + 15) & ~15) + 8 * (int)sizeof(Partials);
@@ -233,17 +211,12 @@ MSA_KFN void block_reduce(Env& env, double* wred, double* out, const int* ops, G
   reduce_block_stage<K>(env, wred, out, ops);
 }
 
-// FOLD = true (kFlagFoldWave; needs both the wave and the pitch part): no separate wave-statistics pass.  The 512
-// own samples of every STFT-512 quad sit in the warp's `xs` tile anyway, so the quad squares them into the SAME
-// 4-sample entries, sums the SAME 20 entries per energy atom in the same order (an atom that straddles two quads is
-// carried as its running sum) and adds the same totals: the segment is read twice instead of three times and the
-// results are bit-identical to the separate pass (fp64 totals are summed in another order).
-template <class Env, class InT, bool FOLD = false>
+template <class Env, class InT>
 MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   constexpr int S = Env::kStates;           // per-lane state copies: 1 on the GPU (registers), 32 in the CPU emulation
   const int T = P.T;
   const int seg = env.cluster_id, r = env.rank, NR = env.nranks, NW = env.nwarps;
-  const FeatLayout lay = feat_layout(T, NR, NW, FOLD);
+  const FeatLayout lay = feat_layout(T, NR, NW);
   const InT* x = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T;
 
   c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
@@ -254,7 +227,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   double* rout = reinterpret_cast<double*>(smem + lay.out_off);
   Partials* part = reinterpret_cast<Partials*>(smem + lay.part_off);
   int* ctr = reinterpret_cast<int*>(smem + lay.ctr_off);
-  const c32* tw512 = reinterpret_cast<const c32*>(tb->tw512);
   const c32* tw400 = reinterpret_cast<const c32*>(tb->tw400);
 
   // reflect-101 padded signal of torch.stft(center=True, pad_mode="reflect"); 0 outside the padding
@@ -273,337 +245,107 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   // groups of 640 samples (8 atoms of 80): lane l loads float4 j at sample 128 j + 4 l, a 160-entry
   // shared-memory tile per group turns the per-lane partial sums into per-atom sums (20 entries each)
   int n_atoms_local = 0;
-  // FOLD: the same totals, accumulated by the STFT-512 quads below
-  double f_tot[S], f_noi[S], f_left[S];
-  float f_amax[S], f_carry[S];
-  for (int i = 0; i < S; ++i) { f_tot[i] = f_noi[i] = f_left[i] = 0.0; f_amax[i] = f_carry[i] = 0.0f; }
-  if constexpr (!FOLD) {
-    double e_tot[S], e_noi[S], e_left[S];
-    float a_max[S];
-    for (int i = 0; i < S; ++i) { e_tot[i] = e_noi[i] = e_left[i] = 0.0; a_max[i] = 0.0f; }
-    if (P.parts & kPartWave) {
-      const int nG = ceil_div(T, kGroup);
-      const int gper = ceil_div(nG, NR);
-      const int g0 = (r * gper < nG) ? r * gper : nG;
-      const int g1 = (g0 + gper < nG) ? g0 + gper : nG;
-      const int full_atoms = T / kAtom;
-      const int a_lo = g0 * 8;
-      const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
-      n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
-      float* scr = reinterpret_cast<float*>(wbuf);
-      // kK1Groups groups of 640 samples are in flight per warp and step: this phase is pure load latency
-      for (int gp = g0 + kK1Groups * env.warp; gp < g1; gp += kK1Groups * NW) {
-        const int ng = (g1 - gp < kK1Groups) ? g1 - gp : kK1Groups;
-        // every 4 consecutive samples form one partial sum (entry = sample offset / 4 of the kK1Groups * 640 samples of
-        // the step); an atom is 20 consecutive entries.  fp32 input: one 16-byte load per entry; int16 input: one
-        // 16-byte load per TWO entries, so the bytes in flight (what this phase lives on) stay the same.  Entries are
-        // formed and added identically for both input types (bit-identical results).
-        env.lanes([&](int lane, int li) {
-          constexpr int kPer = (sizeof(InT) == 2) ? 8 : 4;                       // samples per load
-          constexpr int kLoads = kK1Groups * kGroup / (32 * kPer);               // loads per lane and step
-          float v[kLoads][kPer];
-          const int first = gp * kGroup, limit = (gp + ng) * kGroup;             // samples of this step
-#pragma unroll
-          for (int k = 0; k < kLoads; ++k) {
-            const int off = 32 * kPer * k + kPer * lane;
-            if (first + off < limit) env.ldv(x, first + off, T, v[k]);
-            else {
-#pragma unroll
-              for (int i = 0; i < kPer; ++i) v[k][i] = 0.0f;
-            }
-          }
-          double tot = 0.0;
-#pragma unroll
-          for (int k = 0; k < kLoads; ++k)
-#pragma unroll
-            for (int h4 = 0; h4 < kPer / 4; ++h4) {
-              const float* q = v[k] + 4 * h4;
-              const float sq = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
-              scr[(32 * kPer * k + kPer * lane) / 4 + h4] = sq;
-              tot += (double)sq;
-            }
-          e_tot[li] += tot;
-        });
-        env.wsync();
-        env.lanes([&](int lane, int li) {
-          if (lane < 8 * ng) {
-            const int a = gp * 8 + lane;
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
-            if (a < full_atoms) {
-              atoms[a - a_lo] = s;
-              a_max[li] = fmaxf(a_max[li], s);
-            } else {
-              e_left[li] += (double)s;                     // the T mod 80 samples behind the last full atom
-            }
-          }
-        });
-        env.wsync();
-      }
-      // noise power: first and last int(0.05 T) samples (audio_analyzer.py:282-285), split over the ranks
-      const int nn = P.noise_n;
-      const int per = ceil_div(2 * nn, NR);
-      const int i0 = (r * per < 2 * nn) ? r * per : 2 * nn;
-      const int i1 = (i0 + per < 2 * nn) ? i0 + per : 2 * nn;
-      // exact squares summed in fp64: which lane visits which sample depends on the cluster size and the CTA shape,
-      // and the result must not (a float running sum per lane would differ in its last bits)
+  double e_tot[S], e_noi[S], e_left[S];
+  float a_max[S];
+  for (int i = 0; i < S; ++i) { e_tot[i] = e_noi[i] = e_left[i] = 0.0; a_max[i] = 0.0f; }
+  if (P.parts & kPartWave) {
+    const int nG = ceil_div(T, kGroup);
+    const int gper = ceil_div(nG, NR);
+    const int g0 = (r * gper < nG) ? r * gper : nG;
+    const int g1 = (g0 + gper < nG) ? g0 + gper : nG;
+    const int full_atoms = T / kAtom;
+    const int a_lo = g0 * 8;
+    const int a_hi = (g1 * 8 < full_atoms) ? g1 * 8 : full_atoms;
+    n_atoms_local = (a_hi > a_lo) ? a_hi - a_lo : 0;
+    float* scr = reinterpret_cast<float*>(wbuf);
+    // kK1Groups groups of 640 samples are in flight per warp and step: this phase is pure load latency
+    for (int gp = g0 + kK1Groups * env.warp; gp < g1; gp += kK1Groups * NW) {
+      const int ng = (g1 - gp < kK1Groups) ? g1 - gp : kK1Groups;
+      // every 4 consecutive samples form one partial sum (entry = sample offset / 4 of the kK1Groups * 640 samples of
+      // the step); an atom is 20 consecutive entries.  fp32 input: one 16-byte load per entry; int16 input: one
+      // 16-byte load per TWO entries, so the bytes in flight (what this phase lives on) stay the same.  Entries are
+      // formed and added identically for both input types (bit-identical results).
       env.lanes([&](int lane, int li) {
-        double acc = 0.0;
-        for (int i = i0 + env.warp * 32 + lane; i < i1; i += env.nthreads) {
-          const double v = (double)env.ld(x + ((i < nn) ? i : T - 2 * nn + i));
-          acc += v * v;
+        constexpr int kPer = (sizeof(InT) == 2) ? 8 : 4;                       // samples per load
+        constexpr int kLoads = kK1Groups * kGroup / (32 * kPer);               // loads per lane and step
+        float v[kLoads][kPer];
+        const int first = gp * kGroup, limit = (gp + ng) * kGroup;             // samples of this step
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k) {
+          const int off = 32 * kPer * k + kPer * lane;
+          if (first + off < limit) env.ldv(x, first + off, T, v[k]);
+          else {
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) v[k][i] = 0.0f;
+          }
         }
-        e_noi[li] = acc;
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < kLoads; ++k)
+#pragma unroll
+          for (int h4 = 0; h4 < kPer / 4; ++h4) {
+            const float* q = v[k] + 4 * h4;
+            const float sq = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
+            scr[(32 * kPer * k + kPer * lane) / 4 + h4] = sq;
+            tot += (double)sq;
+          }
+        e_tot[li] += tot;
       });
+      env.wsync();
+      env.lanes([&](int lane, int li) {
+        if (lane < 8 * ng) {
+          const int a = gp * 8 + lane;
+          float s = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 20; ++j) s += scr[20 * lane + j];
+          if (a < full_atoms) {
+            atoms[a - a_lo] = s;
+            a_max[li] = fmaxf(a_max[li], s);
+          } else {
+            e_left[li] += (double)s;                     // the T mod 80 samples behind the last full atom
+          }
+        }
+      });
+      env.wsync();
     }
-    // per-warp totals go to scratch slots 4..7 WITHOUT a barrier: every warp moves on to its STFT-512 quads as
-    // soon as its own loads are in (this phase is pure load latency), and the block-level sums are formed together
-    // with the residual's, behind that phase's barrier
-    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    reduce_warp_stage<4>(env, wred, 4, ops, [&](int li, int k) {
-      return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
+    // noise power: first and last int(0.05 T) samples (audio_analyzer.py:282-285), split over the ranks
+    const int nn = P.noise_n;
+    const int per = ceil_div(2 * nn, NR);
+    const int i0 = (r * per < 2 * nn) ? r * per : 2 * nn;
+    const int i1 = (i0 + per < 2 * nn) ? i0 + per : 2 * nn;
+    // exact squares summed in fp64: which lane visits which sample depends on the cluster size and the CTA shape,
+    // and the result must not (a float running sum per lane would differ in its last bits)
+    env.lanes([&](int lane, int li) {
+      double acc = 0.0;
+      for (int i = i0 + env.warp * 32 + lane; i < i1; i += env.nthreads) {
+        const double v = (double)env.ld(x + ((i < nn) ? i : T - 2 * nn + i));
+        acc += v * v;
+      }
+      e_noi[li] = acc;
     });
   }
+  // per-warp totals go to scratch slots 4..7 WITHOUT a barrier: every warp moves on to its STFT-512 quads as
+  // soon as its own loads are in (this phase is pure load latency), and the block-level sums are formed together
+  // with the residual's, behind that phase's barrier
+  const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
+  reduce_warp_stage<4>(env, wred, 4, ops, [&](int li, int k) {
+    return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
+  });
 
-  // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual
+  // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual (tensor cores)
   {
     double ps[S], pq[S], pn[S];
     float pmax[S];
     for (int i = 0; i < S; ++i) { ps[i] = pq[i] = pn[i] = 0.0; pmax[i] = 0.0f; }
     if (P.parts & kPartPitch) {
-      const int nFp = T / kHopP + 1;
-      // hop-blocks that hold output samples: torch.istft keeps padded positions [256, 256 + T); the last
-      // of them can lie one block past the last frame's first block, so quads cover max(frames, blocks)
-      const int nBl = (T - 1 + kNfftP / 2) / kHopP + 1;
-      const int nQ = ceil_div(nFp > nBl ? nFp : nBl, 4);
+      const int nQ = pitch_quads(T);
       const int qper = ceil_div(nQ, NR);
       const int q_begin = (r * qper < nQ) ? r * qper : nQ;
       const int q_end = (q_begin + qper < nQ) ? q_begin + qper : nQ;
-      // every warp owns a contiguous run of this rank's quads and carries the overlap-add tail of a quad
-      // (hop-blocks 4..6, which the next quad starts with) in registers: no barrier, no shared-memory
-      // exchange, and consecutive quads of a warp re-read overlapping samples from L1.  The quad before the
-      // run is computed as a warm-up (only its tail is used).
-      const int wper = ceil_div(q_end - q_begin, NW);
-      const int wq_lo = q_begin + env.warp * wper;
-      const int wq_begin = (wq_lo < q_end) ? wq_lo : q_end;
-      const int wq_end = (wq_begin + wper < q_end) ? wq_begin + wper : q_end;
-      const int wq_first = (wq_begin > 0 && wq_begin < wq_end) ? wq_begin - 1 : wq_begin;
-      float own[S][7][4];
-      for (int i = 0; i < S; ++i)
-        for (int b = 0; b < 7; ++b)
-          for (int j = 0; j < 4; ++j) own[i][b][j] = 0.0f;
-      // the 512 input samples the quad's own hop-blocks are compared with: pass A has them in registers,
-      // every lane parks its 16 in shared memory (lane-private slots, no synchronisation) until the end of the quad
-      float* xs = reinterpret_cast<float*>(smem + lay.mfl_off) + env.warp * (4 * kHopP);
-      for (int it = 0; it <= wper; ++it) {
-        // the barrier is not needed for correctness: it keeps the warps of the CTA in the same code region
-        // (the loop body is ~100 KB of SASS; warps drifting apart thrash the instruction cache)
-        if (!(P.flags & kFlagNoLockstep)) env.sync();
-        const int quad = wq_begin - 1 + it;
-        if (quad < wq_first || quad >= wq_end) continue;
-        const int f0 = 4 * quad;
-        const int s0 = kHopP * f0 - kNfftP / 2;                  // first sample of frame f0
-        const bool interior = (s0 >= 0) && (s0 + 7 * kHopP <= T);
-#ifdef MSA_VAR_PREFETCH
-        // experiment (scripts/build_variant.sh, not in the default build): the 512 samples the NEXT quad of this warp
-        // adds (t = s0 + 896 .. s0 + 1407) are requested now, one 128-byte line per lane, so that their first touch
-        // (from HBM with FOLD, where no statistics pass has read the segment before) overlaps this quad's arithmetic
-        if (quad + 1 < wq_end && s0 + 896 + 512 <= T) {
-          env.lanes([&](int lane, int li) {
-            (void)li;
-            constexpr int kPerLine = 128 / (int)sizeof(InT);
-            if (lane * kPerLine < 512) env.prefetch(x + s0 + 896 + lane * kPerLine);
-          });
-        }
-#endif
-        // pass A of FFT h: frames (f0 + 2h, f0 + 2h + 1) packed as (re, im); rows of 32 samples.  The quad spans
-        // 7 hop-blocks = 28 samples per lane, loaded once and shared by both FFTs (frames overlap by 3/4)
-        env.lanes([&](int lane, int li) {
-          (void)li;
-          float raw[28];
-          if (interior) {
-#pragma unroll
-            for (int i = 0; i < 28; ++i) raw[i] = env.ld(x + s0 + 32 * i + lane);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 28; ++i) raw[i] = xr(s0 + 32 * i + lane);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) xs[32 * i + lane] = raw[i];
-          static_for<0, 2>([&](auto hc) {
-            constexpr int h = decltype(hc)::value;
-            const bool oka = (f0 + 2 * h) < nFp, okb = (f0 + 2 * h + 1) < nFp;
-            c32 z[16];
-            if (interior) {                                        // an interior quad has four valid frames: no selects
-#pragma unroll
-              for (int n1 = 0; n1 < 16; ++n1) {
-                const float w = tb->win512[32 * n1 + lane];
-                z[n1] = c32{w * raw[8 * h + n1], w * raw[8 * h + n1 + 4]};
-              }
-            } else {
-#pragma unroll
-              for (int n1 = 0; n1 < 16; ++n1) {
-                const float w = tb->win512[32 * n1 + lane];
-                z[n1] = c32{oka ? w * raw[8 * h + n1] : 0.0f, okb ? w * raw[8 * h + n1 + 4] : 0.0f};
-              }
-            }
-            pass_a_fwd<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
-          });
-        });
-        env.wsync();
-        // pass B forward = the STFT spectrum X[k1 + 16 k2] of this row; phase_vocoder(rate = 1.0)
-        // returns its input, so the inverse radix-32 follows in the same registers
-        env.lanes([&](int lane, int li) {
-          (void)li;
-          c32* row = wbuf + (lane >> 4) * kFftHalf + (lane & 15) * kRow512;
-          c32 v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = row[i];
-          // the unnormalised inverse DFT is the forward DFT read backwards (y[n] = DFT(X)[(32 - n) mod 32]),
-          // so both directions run the same code (one rolled loop: half the instruction-cache footprint)
-          // and the index reversal is applied once, as register renaming, when the row is written back
-#pragma unroll 1
-          for (int rep = 0; rep < 2; ++rep) dft32<false>(v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) row[i] = v[(32 - i) & 31];
-        });
-        env.wsync();
-        // inverse pass A, synthesis window, overlap-add of the quad's 4 frames in registers: frame f0 + j
-        // covers hop-blocks j .. j+3 of the quad's 7 blocks; blocks 0..2 start from the predecessor's tail
-        env.lanes([&](int lane, int li) {
-          (void)lane;
-#pragma unroll
-          for (int b = 0; b < 3; ++b)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) own[li][b][i] = own[li][4 + b][i];
-#pragma unroll
-          for (int b = 3; b < 7; ++b)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) own[li][b][i] = 0.0f;
-        });
-        for (int h = 0; h < 2; ++h) {
-          env.lanes([&](int lane, int li) {
-            c32 z[16];
-            pass_a_inv<kRow512>(z, tw512, lane, wbuf + h * kFftHalf);
-            static_for<0, 16>([&](auto nc) {
-              constexpr int n1 = decltype(nc)::value;
-              const float w = tb->win512[32 * n1 + lane];    // the 1/512 of the unnormalised inverse lives in ienv
-              if (h == 0) {
-                own[li][n1 / 4][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4][n1 % 4]);
-                own[li][n1 / 4 + 1][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 1][n1 % 4]);
-              } else {
-                own[li][n1 / 4 + 2][n1 % 4] = fmaf(w, z[n1].x, own[li][n1 / 4 + 2][n1 % 4]);
-                own[li][n1 / 4 + 3][n1 % 4] = fmaf(w, z[n1].y, own[li][n1 / 4 + 3][n1 % 4]);
-              }
-            });
-          });
-        }
-        env.wsync();                                             // the tiles are free for the next quad
-        if (quad >= wq_begin) {
-          // finalise blocks 0..3 of the quad: divide by the window envelope and compare with the input
-          // (torch.istft trims the n_fft/2 padding: t = position - 256)
-          const int b0 = 4 * quad;
-          const bool fast = (b0 >= 3) && (b0 + 3 <= nFp - 1) && (kHopP * (b0 + 4) - kNfftP / 2 <= T);
-          env.lanes([&](int lane, int li) {
-            float s1 = 0.0f, s2 = 0.0f, mx = 0.0f;
-            int cnt = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int o = 32 * i + lane;
-                const int t = kHopP * (b0 + b) + o - kNfftP / 2;
-                const float y = own[li][b][i];
-                if (fast) {
-                  const float pv = fabsf(xs[kHopP * b + o] - y * tb->ienv[o]);
-                  s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
-                } else if (t >= 0 && t < T) {
-                  float e = 0.0f;
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int f = b0 + b - j;
-                    if (f >= 0 && f < nFp) { const float w = tb->win512[j * kHopP + o]; e = fmaf(w, w, e); }
-                  }
-                  const float pv = fabsf(xs[kHopP * b + o] - y / (e * (float)kNfftP));
-                  s1 += pv; s2 = fmaf(pv, pv, s2); mx = fmaxf(mx, pv); ++cnt;
-                }
-              }
-            ps[li] += (double)s1; pq[li] += (double)s2; pn[li] += (double)cnt;
-            pmax[li] = fmaxf(pmax[li], mx);
-          });
-        }
-        if constexpr (FOLD) {
-          // wave statistics of the quad's own 512 samples t = 512 quad - 256 + k (still in xs; the FFT tiles are free and
-          // serve as scratch): entries e = E0 .. E0 + 127 of 4 samples each, exactly the entries of the separate pass
-          float* ent = reinterpret_cast<float*>(wbuf);
-          const int E0 = 128 * quad - 64;
-          const bool owned = quad >= wq_begin;                   // the warm-up quad only starts the straddling atom
-          const bool clean = (s0 >= 0) && (s0 + kNfftP <= T);
-          const int nn = P.noise_n;
-          const bool noisy = owned && (4 * E0 < nn || 4 * E0 + kNfftP > T - nn);
-          env.lanes([&](int lane, int li) {
-            double tot = 0.0, noi = 0.0;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int m = lane + 32 * c;
-              const float4 q4 = *reinterpret_cast<const float4*>(xs + 4 * m);
-              float q[4] = {q4.x, q4.y, q4.z, q4.w};
-              const int t = 4 * (E0 + m);
-              if (!clean) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (t + i < 0 || t + i >= T) q[i] = 0.0f;      // xs holds the reflect padding there
-              }
-              const float sq = fmaf(q[3], q[3], fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0])));
-              ent[m] = sq;
-              tot += (double)sq;
-              if (noisy) {
-                // first and last int(0.05 T) samples (audio_analyzer.py:282-285): exact squares summed in fp64
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                  if (t + i < nn || t + i >= T - nn) noi += (double)q[i] * (double)q[i];
-              }
-            }
-            if (owned) { f_tot[li] += tot; f_noi[li] += noi; }
-          });
-          env.wsync();
-          // lane l < 8 continues / forms the l-th atom that overlaps the quad: a sequential fp32 sum over its entries
-          const int full_atoms = T / kAtom;
-          const int a_first = (E0 > 0) ? E0 / 20 : 0;
-          const int a_base = fold_first_atom_of_quad(q_begin);   // first atom this rank stores
-          const bool have_prev = quad > wq_first;                // the previous quad of this warp left its carry
-          env.lanes([&](int lane, int li) {
-            const int a = a_first + lane;
-            const int last = fold_last_entry(a, T);
-            const int lo = (20 * a > E0) ? 20 * a : E0;
-            const int hi = (last < E0 + 127) ? last : E0 + 127;
-            if (lane < 8 && a <= full_atoms && lo <= hi) {
-              float s = (20 * a < E0 && have_prev) ? f_carry[li] : 0.0f;
-              for (int e = lo; e <= hi; ++e) s += ent[e - E0];
-              if (hi < last) {
-                ent[128] = s;                                    // the atom goes on in the next quad
-              } else if (owned) {
-                if (a < full_atoms) {
-                  atoms[a - a_base] = s;
-                  f_amax[li] = fmaxf(f_amax[li], s);
-                } else {
-                  f_left[li] += (double)s;                       // the T mod 80 samples behind the last full atom
-                }
-              }
-            }
-          });
-          env.wsync();
-          env.lanes([&](int lane, int li) { (void)lane; f_carry[li] = ent[128]; });
-          env.wsync();                                           // the tiles are free again
-        }
-      }
-    }
-    if constexpr (FOLD) {
-      const int opsw[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-      reduce_warp_stage<4>(env, wred, 4, opsw, [&](int li, int k) {
-        return k == 0 ? f_tot[li] : (k == 1 ? f_noi[li] : (k == 2 ? f_left[li] : (double)f_amax[li]));
-      });
+      // msa_pitch_tc.cuh: every warp owns a contiguous run of this rank's quads; its fp16 ring of the padded signal is
+      // the warp's own buffer (the wave-statistics scratch of the same warp is dead by now: program order)
+      env.wsync();
+      pitch_tc<Env, InT>(env, x, T, q_begin, q_end, reinterpret_cast<uint16_t*>(wbuf), &tb->pt, &P.tab->pr, ps, pq, pn, pmax);
     }
     const int ops[8] = {kOpSum, kOpSum, kOpSum, kOpMax, kOpSum, kOpSum, kOpSum, kOpMax};
     reduce_warp_stage<4>(env, wred, 0, ops, [&](int li, int k) {
@@ -1041,14 +783,8 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       env.lanes([&](int lane, int li) {
         (void)li;
         for (int a = env.warp * 32 + lane; a < nA; a += env.nthreads) {
-          if constexpr (FOLD) {
-            const int qpr = fold_quads_per_rank(T, NR);
-            const int rr = ((20 * a + 83) >> 7) / qpr;             // the rank whose quad finished the atom
-            all_atoms[a] = env.remote(atoms, rr)[a - fold_first_atom_of_quad(rr * qpr)];
-          } else {
-            const int rr = a / (8 * gper_a);
-            all_atoms[a] = env.remote(atoms, rr)[a - 8 * gper_a * rr];
-          }
+          const int rr = a / (8 * gper_a);
+          all_atoms[a] = env.remote(atoms, rr)[a - 8 * gper_a * rr];
         }
       });
     }
@@ -1219,7 +955,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
             d[68] = dg[li][3]; d[69] = dg[li][4]; d[70] = dg[li][5]; d[71] = (float)nG;
             d[72] = dg[li][6]; d[73] = (float)nBk; d[74] = (float)nA;
             d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
-            d[79] = FOLD ? 1.0f : 0.0f;                      // which variant produced the row
+            d[79] = 0.0f;
           }
           if (lane < kDetailStride - 80) d[80 + lane] = 0.0f;
         }

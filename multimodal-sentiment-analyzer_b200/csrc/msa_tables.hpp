@@ -31,19 +31,56 @@ constexpr int kMelTrips = kMelTrip0 + kMelTrip1 + kMelTrip2 + kMelTrip3;   // 17
 constexpr int kDctQuads = 13;                            // 4 slots x 13 coefficients = 52 floats = 13 float4 per lane
 constexpr int kPowStride = 208;                          // power spectrum row: 201 bins + zero pad for the mel trips
 
+// fp32 -> fp16 bits, round to nearest even (host-side table construction; the values are all in [-1, 1])
+inline uint16_t f32_to_f16_bits(float f) {
+  uint32_t x;
+  std::memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((x >> 23) & 0xffu) - 127 + 15;
+  uint32_t m = x & 0x7fffffu;
+  if (e >= 31) return (uint16_t)(sign | 0x7bffu);                       // saturate (never reached by the tables)
+  if (e <= 0) {                                                          // subnormal half or zero
+    if (e < -10) return (uint16_t)sign;
+    m |= 0x800000u;
+    const int shift = 14 - e;                                            // 14 .. 24
+    uint32_t h = m >> shift;
+    const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return (uint16_t)(sign | h);
+  }
+  uint32_t h = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;               // may carry into the exponent: still correct
+  return (uint16_t)(sign | h);
+}
+inline uint32_t f16x2_bits(double lo, double hi) {
+  return (uint32_t)f32_to_f16_bits((float)lo) | ((uint32_t)f32_to_f16_bits((float)hi) << 16);
+}
+
+// Constant FRAGMENTS of the tensor-core STFT-512 round trip (msa_pitch_tc.cuh): every entry is the fp16 pair one lane
+// (g = lane / 4, t = lane % 4) of a warp holds in one register of an mma.sync m16n8k16 operand, so the kernel reads
+// them with one conflict-free vector load per lane.  512 = 16 x 32, n = 32 n1 + n2, k = k1 + 16 k2.
+struct alignas(16) PitchSmemTables {      // read inside the frame loop
+  uint32_t cs[16][32][2];                 // [8 sin + 4 ks + m][lane] B fragment (rows 16 ks + .., columns 8 m + g) of cos|sin(2 pi r c / 32) / 16
+  uint32_t ws[4][32][4];                  // [i][lane][j] synthesis window pair at n1 = (g + 4 i) % 16, n2 = 8 j + 2 t
+  uint32_t a4[4][32][4];                  // [Vre^0, -Vim^0, Vre^1, Vim^1][lane] A fragments of exp(+2 pi i n1 k1 / 16) / 2, rows rho = (n1 + 4 a) % 16
+};
+struct alignas(16) PitchRegTables {       // read once per work item into registers
+  uint32_t a1[3][32][4];                  // [cos, -sin, +sin][lane] A fragments of W_16^(k1 n1)
+  uint32_t tw[8][32][2];                  // [2 j + h][lane] {cos, sin}(2 pi k1 n2 / 512) pairs, k1 = g + 8 h, n2 = 8 j + 2 t
+  uint32_t wa[4][32][2];                  // [j][lane] analysis window pairs in B-fragment order (rows n1 = 2 t.., column n2 = 8 j + g)
+};
+
 // The part every CTA stages in shared memory (copied as 16-byte words: keep the size a multiple of 16).
 struct alignas(16) SmemTables {
-  float tw512[2 * 15 * 32];       // [(k1-1)*32 + n2] = W_512^(n2 k1) as (cos, -sin)
   float tw400[2 * 15 * 32];       // [(k1-1)*32 + n2] = W_400^(n2 k1), n2 < 25
   float win400[kNfftM];
-  float win512[kNfftP];
-  float ienv[kHopP];              // 1 / (512 sum_j win512[j*128 + o]^2): interior window envelope of torch.istft
-                                  // times the 1/512 of the unnormalised inverse FFT (exact: power of two)
   float mel_w[kMelTrips * 32];    // [(trip offset of slot s + p)*32 + lane], zero padded
   float dctq[kDctQuads * 32 * 4]; // float4 [i*32 + lane]: flattened (slot, k) = divmod(4 i + c, 13); 0 for empty filters
   float dct_dead[16];             // sum over the empty filters of dct[m][k]
   uint16_t mel_lo[4 * 32];        // first bin of filter 32 s + lane (0 for the empty filters)
   uint16_t mel_dead[4 * 32];      // 1 where the filter has no non-zero weight
+  PitchSmemTables pt;
 };
 static_assert(sizeof(SmemTables) % 16 == 0, "SmemTables is copied as int4");
 
@@ -51,6 +88,7 @@ static_assert(sizeof(SmemTables) % 16 == 0, "SmemTables is copied as int4");
 struct FeatureTables {
   SmemTables s;
   float dct[kMels * 16];          // plain [m][k] table (tests / reference restatement)
+  PitchRegTables pr;
   int mel_nnz;
   int pad[3];
 };
@@ -60,17 +98,8 @@ inline int build_feature_tables(FeatureTables& ft) {
   SmemTables& t = ft.s;
   const double PI = 3.14159265358979323846;
   for (int n = 0; n < kNfftM; ++n) t.win400[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftM));
-  for (int n = 0; n < kNfftP; ++n) t.win512[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP));
-  for (int o = 0; o < kHopP; ++o) {
-    float e = 0.0f;
-    for (int j = 0; j < 4; ++j) e += t.win512[j * kHopP + o] * t.win512[j * kHopP + o];
-    t.ienv[o] = (1.0f / e) * (1.0f / (float)kNfftP);
-  }
   for (int k1 = 1; k1 < 16; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
-      const double a = 2.0 * PI * (double)(n2 * k1) / 512.0;
-      t.tw512[2 * ((k1 - 1) * 32 + n2)] = (float)std::cos(a);
-      t.tw512[2 * ((k1 - 1) * 32 + n2) + 1] = (float)(-std::sin(a));
       const double b = 2.0 * PI * (double)((n2 < 25 ? n2 : 0) * k1) / 400.0;
       t.tw400[2 * ((k1 - 1) * 32 + n2)] = (float)std::cos(b);
       t.tw400[2 * ((k1 - 1) * 32 + n2) + 1] = (float)(-std::sin(b));
@@ -117,6 +146,63 @@ inline int build_feature_tables(FeatureTables& ft) {
     }
   }
   ft.mel_nnz = nnz;
+  // ---- fragments of the tensor-core STFT-512 round trip
+  auto hann = [&](int n) { return 0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP); };
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, tq = lane & 3;
+    for (int sn = 0; sn < 2; ++sn)
+      for (int ks = 0; ks < 2; ++ks)
+        for (int m = 0; m < 4; ++m) {
+          auto v = [&](int row) {                                      // matrix [n2 or k2][k2 or n2], symmetric
+            const double a = 2.0 * PI * (double)((row * (8 * m + g)) % 32) / 32.0;
+            return (sn ? std::sin(a) : std::cos(a)) / 16.0;
+          };
+          uint32_t* o = t.pt.cs[sn * 8 + ks * 4 + m][lane];
+          o[0] = f16x2_bits(v(16 * ks + 2 * tq), v(16 * ks + 2 * tq + 1));
+          o[1] = f16x2_bits(v(16 * ks + 2 * tq + 8), v(16 * ks + 2 * tq + 9));
+        }
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        const int n = 32 * ((g + 4 * i) % 16) + 8 * j + 2 * tq;
+        t.pt.ws[i][lane][j] = f16x2_bits(hann(n), hann(n + 1));
+      }
+    for (int f = 0; f < 4; ++f) {
+      const int a = f >> 1;                                            // rotation of the output rows: rho = (n1 + 4 a) % 16
+      auto v = [&](int rho, int k1) {
+        const int n1 = (rho - 4 * a + 16) % 16;
+        const double ang = 2.0 * PI * (double)((n1 * k1) % 16) / 16.0;
+        const double c = std::cos(ang) * 0.5, s = std::sin(ang) * 0.5;
+        return f == 0 ? c : (f == 1 ? -s : (f == 2 ? c : s));
+      };
+      uint32_t* o = t.pt.a4[f][lane];
+      o[0] = f16x2_bits(v(g, 2 * tq), v(g, 2 * tq + 1));
+      o[1] = f16x2_bits(v(g + 8, 2 * tq), v(g + 8, 2 * tq + 1));
+      o[2] = f16x2_bits(v(g, 2 * tq + 8), v(g, 2 * tq + 9));
+      o[3] = f16x2_bits(v(g + 8, 2 * tq + 8), v(g + 8, 2 * tq + 9));
+    }
+    for (int f = 0; f < 3; ++f) {
+      auto v = [&](int k1, int n1) {
+        const double ang = 2.0 * PI * (double)((n1 * k1) % 16) / 16.0;
+        return f == 0 ? std::cos(ang) : (f == 1 ? -std::sin(ang) : std::sin(ang));
+      };
+      uint32_t* o = ft.pr.a1[f][lane];
+      o[0] = f16x2_bits(v(g, 2 * tq), v(g, 2 * tq + 1));
+      o[1] = f16x2_bits(v(g + 8, 2 * tq), v(g + 8, 2 * tq + 1));
+      o[2] = f16x2_bits(v(g, 2 * tq + 8), v(g, 2 * tq + 9));
+      o[3] = f16x2_bits(v(g + 8, 2 * tq + 8), v(g + 8, 2 * tq + 9));
+    }
+    for (int j = 0; j < 4; ++j) {
+      for (int h = 0; h < 2; ++h) {
+        const int k1 = g + 8 * h, n2 = 8 * j + 2 * tq;
+        const double a0 = 2.0 * PI * (double)(k1 * n2) / 512.0, a1 = 2.0 * PI * (double)(k1 * (n2 + 1)) / 512.0;
+        ft.pr.tw[2 * j + h][lane][0] = f16x2_bits(std::cos(a0), std::cos(a1));
+        ft.pr.tw[2 * j + h][lane][1] = f16x2_bits(std::sin(a0), std::sin(a1));
+      }
+      const int n2 = 8 * j + g;
+      ft.pr.wa[j][lane][0] = f16x2_bits(hann(32 * (2 * tq) + n2), hann(32 * (2 * tq + 1) + n2));
+      ft.pr.wa[j][lane][1] = f16x2_bits(hann(32 * (2 * tq + 8) + n2), hann(32 * (2 * tq + 9) + n2));
+    }
+  }
   return bad;   // 0 when the compile-time trip counts match the filter bank
 }
 

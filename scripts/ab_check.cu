@@ -111,9 +111,30 @@ int main(int argc, char** argv) {
         continue;
       }
       int bad_rows = 0;
-      for (int b = 0; b < cs.B; ++b)
-        bad_rows += memcmp(&hf[0][b * 31], &hf[1][b * 31], 31 * 4) != 0 || memcmp(&hd[0][b * 96], &hd[1][b * 96], 79 * 4) != 0 ||
-                    memcmp(&hd[0][b * 96 + 80], &hd[1][b * 96 + 80], 16 * 4) != 0;   // [79] names the variant that made the row
+      // MSA_AB_PITCH_TOL=1: the libraries compute the STFT-512 round trip differently (fp32 FFT vs fp16 tensor cores), so the
+      // "pitch" slot (rounding residue, |v| <= 1e-6 by contract), its residual diagnostics [65:68] and - without
+      // STRICT_NAN, where the LayerNorm row is finite - the LayerNorm entries are compared with an absolute tolerance
+      static const bool pitch_tol = getenv("MSA_AB_PITCH_TOL") && getenv("MSA_AB_PITCH_TOL")[0] == '1';
+      for (int b = 0; b < cs.B; ++b) {
+        if (!pitch_tol) {
+          bad_rows += memcmp(&hf[0][b * 31], &hf[1][b * 31], 31 * 4) != 0 || memcmp(&hd[0][b * 96], &hd[1][b * 96], 79 * 4) != 0 ||
+                      memcmp(&hd[0][b * 96 + 80], &hd[1][b * 96 + 80], 16 * 4) != 0;   // [79] names the variant that made the row
+          continue;
+        }
+        bool bad = false;
+        for (int k = 0; k < 31; ++k) {
+          const float a = hf[0][b * 31 + k], c = hf[1][b * 31 + k];
+          bad = bad || !(fabsf(a - c) <= 2e-6f);
+        }
+        for (int k = 0; k < 79; ++k) {
+          const float a = hd[0][b * 96 + k], c = hd[1][b * 96 + k];
+          if (k == 65 || k == 66 || k == 67) continue;
+          const bool loose = (k == 8) || (k >= 32 && k < 63);
+          if (loose) bad = bad || !((a != a && c != c) || fabsf(a - c) <= 2e-6f);
+          else bad = bad || memcmp(&a, &c, 4) != 0;
+        }
+        bad_rows += bad;
+      }
       bad_total += bad_rows + (rc != 0);
       printf("%s%d", l > 1 ? ", " : "", bad_rows);
     }
@@ -143,6 +164,24 @@ int main(int argc, char** argv) {
           printf("%s\"%s_%s_lib%d_%d\": %.4f", first ? "" : ", ", silence ? "silence" : "voiced", is16 ? "s16" : "f32", l, rep, ms / 20.0f);
           first = false;
         }
+  }
+  // per-part cost (C-ABI parts mask: 1 wave statistics, 2 MFCC, 4 STFT-512 round trip), fp32 input, voiced batch
+  synth_kernel<<<592, 256>>>(pcm, wav, emo, 1024, 80000, 0);
+  CK(cudaDeviceSynchronize());
+  {
+    const int pm[] = {0, 1, 2, 4, 3, 5, 6, 7};
+    for (int pi = 0; pi < 8; ++pi)
+      for (int l = 0; l < nlib; ++l) {
+        for (int i = 0; i < 3; ++i) f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], pm[pi], 0, nullptr);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < 20; ++i) f32[l](wav, 1024, 80000, nullptr, feat, nullptr, nullptr, tflags[l], pm[pi], 0, nullptr);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.0f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        printf(", \"parts%d_f32_lib%d\": %.4f", pm[pi], l, ms / 20.0f);
+      }
   }
   // streaming shape: one segment over a cluster of 8 CTAs (auto), 200 launches
   for (int l = 0; l < nlib; ++l) {

@@ -57,6 +57,65 @@ struct CpuEnv {
   }
   void ldv(const float* x, int idx, int T, float* v) { ld4(x, idx, T, v); }
   void ldv(const int16_t* x, int idx, int T, float* v) { ld4(x, idx, T, v); ld4(x, idx + 4, T, v + 4); }
+  // ---- tensor-core primitives of msa_pitch_tc.cuh, emulated over the 32 per-lane register copies
+  uint32_t ldu(const uint32_t* p) { return *p; }
+  float cospi(float v) { return (float)std::cos(3.14159265358979323846 * (double)v); }
+  template <class InT> void ld16(const InT* x, int idx, float* v) { for (int i = 0; i < 16; ++i) v[i] = ld(x + idx + i); }
+  void st16(uint16_t* dst, const uint32_t* w) { std::memcpy(dst, w, 32); }
+  uint32_t lds1(const uint32_t* p) { return *p; }
+  void lds2(uint32_t* d, const uint32_t* p) { d[0] = p[0]; d[1] = p[1]; }
+  void lds4(uint32_t* d, const uint32_t* p) { for (int i = 0; i < 4; ++i) d[i] = p[i]; }
+  static float h16(uint32_t v, int hi) { return hi ? msa::h2_hi(v) : msa::h2_lo(v); }
+  template <class D, class A, class B> void mma(D dg, A ag, B bg, bool accumulate) {
+    float Am[16][16], Bm[16][8], Cm[16][8];
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      const uint32_t* a = ag(l);
+      const uint32_t* b = bg(l);
+      const uint32_t* c = dg(l);
+      for (int e = 0; e < 2; ++e) {
+        Am[g][2 * t + e] = h16(a[0], e); Am[g + 8][2 * t + e] = h16(a[1], e);
+        Am[g][2 * t + 8 + e] = h16(a[2], e); Am[g + 8][2 * t + 8 + e] = h16(a[3], e);
+        Bm[2 * t + e][g] = h16(b[0], e); Bm[2 * t + 8 + e][g] = h16(b[1], e);
+        Cm[g][2 * t + e] = accumulate ? h16(c[0], e) : 0.0f; Cm[g + 8][2 * t + e] = accumulate ? h16(c[1], e) : 0.0f;
+      }
+    }
+    float Dm[16][8];
+    for (int i = 0; i < 16; ++i)
+      for (int j = 0; j < 8; ++j) {
+        float s = Cm[i][j];
+        for (int k = 0; k < 16; ++k) s += Am[i][k] * Bm[k][j];
+        Dm[i][j] = s;
+      }
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      uint32_t* d = dg(l);
+      d[0] = msa::h2_pack(Dm[g][2 * t], Dm[g][2 * t + 1]);
+      d[1] = msa::h2_pack(Dm[g + 8][2 * t], Dm[g + 8][2 * t + 1]);
+    }
+  }
+  template <class R, class P> void ldsm4t(R rg, P pg) {
+    for (int m = 0; m < 4; ++m) {
+      uint16_t tile[8][8];
+      for (int r = 0; r < 8; ++r) std::memcpy(tile[r], pg(8 * m + r), 16);
+      for (int l = 0; l < 32; ++l) {
+        const int g = l >> 2, t = l & 3;
+        rg(l)[m] = (uint32_t)tile[2 * t][g] | ((uint32_t)tile[2 * t + 1][g] << 16);     // transposed distribution
+      }
+    }
+  }
+  template <class D> void movmt(D dg) {
+    uint16_t tile[8][8];
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      const uint32_t v = dg(l)[0];
+      tile[g][2 * t] = (uint16_t)(v & 0xffffu); tile[g][2 * t + 1] = (uint16_t)(v >> 16);
+    }
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      dg(l)[0] = (uint32_t)tile[2 * t][g] | ((uint32_t)tile[2 * t + 1][g] << 16);
+    }
+  }
   void copy16(void* dst, const void* src, int bytes) {
     if (warp == 0) std::memcpy(dst, src, bytes);
   }
@@ -97,9 +156,7 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
   FeatParams P{};
   P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.noise_n = (int)(0.05 * (double)T);
   P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.dbscratch = dbscratch; P.tab = &tab; P.flags = flags; P.parts = parts;
-  // kFlagFoldWave: the wave statistics ride on the STFT-512 quads (needs both parts), like the launcher decides it
-  const bool fold = (flags & kFlagFoldWave) && (parts & kPartWave) && (parts & kPartPitch);
-  const FeatLayout lay = feat_layout(T, nranks, nwarps, fold);
+  const FeatLayout lay = feat_layout(T, nranks, nwarps);
   for (int seg = 0; seg < B; ++seg) {
     CpuCluster cl(nranks * nwarps);
     std::vector<std::unique_ptr<unsigned char[]>> mem;
@@ -115,13 +172,8 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
       for (int w = 0; w < nwarps; ++w)
         th.emplace_back([&, r, w]() {
           CpuEnv env{w * 32, nwarps * 32, 0, w, nwarps, r, nranks, seg, bars[r].get(), &cl};
-          if (fold) {
-            if (is_s16) features_cta<CpuEnv, int16_t, true>(env, P, cl.smem[r]);
-            else features_cta<CpuEnv, float, true>(env, P, cl.smem[r]);
-          } else {
-            if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
-            else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
-          }
+          if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
+          else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
         });
     for (auto& t : th) t.join();
   }
@@ -142,25 +194,26 @@ extern "C" void emu_dft(int n, int inverse, const float* in, float* out) {
   for (int i = 0; i < n; ++i) { out[2 * i] = v[i].x; out[2 * i + 1] = v[i].y; }
 }
 
-// full two-pass transform of one complex vector of 512 or 400 points through the tile layout
+// full two-pass transform of one complex vector of 400 points through the tile layout
 extern "C" int emu_fft(int n, const float* in, float* out) {
   using namespace msa;
   static FeatureTables tab;
   static bool built = false;
   if (!built) { if (build_feature_tables(tab) != 0) return -100; built = true; }
+  if (n != 400) return -1;
   std::vector<c32> tile(kFftHalf);
   const int n2 = n / 16;
-  const c32* tw = reinterpret_cast<const c32*>(n == 512 ? tab.s.tw512 : tab.s.tw400);
+  const c32* tw = reinterpret_cast<const c32*>(tab.s.tw400);
   for (int lane = 0; lane < n2; ++lane) {
     c32 z[16];
     for (int n1 = 0; n1 < 16; ++n1) z[n1] = c32{in[2 * (n2 * n1 + lane)], in[2 * (n2 * n1 + lane) + 1]};
-    if (n == 512) pass_a_fwd<kRow512>(z, tw, lane, tile.data()); else pass_a_fwd<kRow400>(z, tw, lane, tile.data());
+    pass_a_fwd<kRow400>(z, tw, lane, tile.data());
   }
   for (int k1 = 0; k1 < 16; ++k1) {
     c32 v[32];
-    c32* row = tile.data() + k1 * (n == 512 ? kRow512 : kRow400);
+    c32* row = tile.data() + k1 * kRow400;
     for (int i = 0; i < n2; ++i) v[i] = row[i];
-    if (n == 512) dft32<false>(v); else dft25<false>(v);
+    dft25<false>(v);
     for (int k2 = 0; k2 < n2; ++k2) { out[2 * (k1 + 16 * k2)] = v[k2].x; out[2 * (k1 + 16 * k2) + 1] = v[k2].y; }
   }
   return 0;

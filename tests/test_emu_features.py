@@ -44,6 +44,15 @@ def run(lib, x, nranks=4, nwarps=4, flags=1, parts=7, emo=None, scratch=False):
     return feat, det, dbg
 
 
+def residual_is_fp16_noise(det, x):
+    """The STFT -> ISTFT round trip runs in fp16 on the tensor cores (msa_pitch_tc.cuh): |x - x^| (det[65:68] = mean,
+    std, max) must be fp16 rounding noise relative to the signal.  One wrong index anywhere in the four matrix stages,
+    the twiddles, the transposes or the overlap-add ring gives a residual of the order of the signal itself."""
+    amp = float(np.abs(x).max())
+    assert det[67] <= 6e-3 * amp + 2e-6, (det[65:68], amp)
+    assert det[66] <= 2e-3 * amp + 1e-6, (det[65:68], amp)
+
+
 def check_against_oracle(det, feat, x, emo=None, rel=1e-3, floor=1e-5):
     """Tolerances of SURVEY.md section 8(d): rel 1e-3 (abs floor), pitch abs 1e-6, exact flags."""
     raw = fx.raw_features(x, emo)
@@ -73,7 +82,7 @@ def test_seeded_segment_all_cluster_sizes(emu, nranks, nwarps):
     check_against_oracle(det[0], feat[0], x)
     ref = fx.mfcc(x.astype(np.float64)).T
     assert np.abs(dbg[0] - ref).max() < 1e-3                                # MFCC matrix itself (values up to ~170)
-    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6                          # STFT->ISTFT residual: std, max
+    residual_is_fp16_noise(det[0], x)
 
 
 def test_int16_ingest_matches_f32(emu):
@@ -122,7 +131,7 @@ def test_every_sample_is_reconstructed_once(emu, T, nranks):
     x = synth.pcm_to_f32(synth.segment_pcm(77, T))
     feat, det, _ = run(emu, x[None], nranks, 4)
     assert det[0, 72] == T
-    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6
+    residual_is_fp16_noise(det[0], x)
     check_against_oracle(det[0], feat[0], x)
 
 
@@ -169,57 +178,3 @@ def test_results_do_not_depend_on_the_partition(emu, name):
             assert np.array_equal(cur[2], ref[2]), (nranks, nwarps)
     if name == "path_flip":
         assert (1.0, 0.0) in paths and (1.0, 1.0) in paths           # both the patch-list and the clamped-pass path ran
-
-
-@pytest.mark.parametrize("case", ["seg1234", "half_silence", "odd_12345", "short_500", "T257", "T513", "T30001", "T80129", "T79920"])
-def test_fold_wave_statistics_into_the_stft_quads(emu, case):
-    """MSA_FEAT_FOLD_WAVE (flag 4): the STFT-512 quads form the energy atoms, totals and noise energy from the samples
-    they hold, instead of the separate wave-statistics pass.  Entries, atoms and their summation order are the same, so
-    every output (rows, raw features, LayerNorm row, MFCC matrix, diagnostics) must be bit-identical for every segment
-    length (ragged last atom, atoms straddling quads, warps and ranks) and cluster shape; detail[79] tells the variant."""
-    if case == "seg1234":
-        x = synth.pcm_to_f32(synth.segment_pcm(1234))
-    elif case.startswith("T"):
-        x = synth.pcm_to_f32(synth.segment_pcm(77, int(case[1:])))
-    else:
-        x = synth.adversarial_cases()[case]
-    for nranks, nwarps in ((1, 8), (2, 4), (4, 3), (8, 8), (1, 2)):
-        f0, d0, g0 = run(emu, x[None], nranks, nwarps, flags=1)
-        f1, d1, g1 = run(emu, x[None], nranks, nwarps, flags=1 | 4)
-        assert d0[0, 79] == 0.0 and d1[0, 79] == 1.0
-        assert np.array_equal(f0, f1)
-        assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True), (nranks, nwarps)
-        assert np.array_equal(g0, g1)
-    # int16 ingest takes the same route
-    pcm = np.round(x * 32768.0).astype(np.int16)
-    f2, d2, _ = run(emu, pcm[None], 2, 4, flags=1 | 4)
-    f3, d3, _ = run(emu, pcm[None], 2, 4, flags=1)
-    assert d2[0, 79] == 1.0 and np.array_equal(f2, f3) and np.array_equal(d2[:, :79], d3[:, :79], equal_nan=True)
-
-
-def test_fold_needs_both_parts(emu):
-    """Without the STFT-512 part there are no quads to ride on: the separate pass runs (detail[79] = 0), same results."""
-    x = synth.pcm_to_f32(synth.segment_pcm(1234))
-    _, d0, _ = run(emu, x[None], 2, 4, flags=1, parts=3)
-    _, d1, _ = run(emu, x[None], 2, 4, flags=1 | 4, parts=3)
-    assert d1[0, 79] == 0.0
-    assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True)
-
-
-def test_fold_sweep_of_lengths_and_shapes(emu):
-    """Every length around the atom (80), entry (4), quad (512) and frame boundaries, random cluster shapes:
-    the folded statistics give the default kernel's bits."""
-    rng = np.random.default_rng(7)
-    lengths = list(range(257, 290)) + [320, 339, 340, 399, 400, 401, 511, 512, 575, 576, 767, 768, 769, 1279, 1280, 1281, 1599, 1600,
-                                       2047, 2048, 5119, 5120, 5121] + [int(t) for t in rng.integers(300, 9000, 12)]
-    for n, T in enumerate(lengths):
-        x = (rng.standard_normal(T) * 3000).astype(np.int16)
-        if n % 5 == 0:
-            x[T // 3: T // 2] = 0
-        nranks, nwarps = int(rng.choice([1, 2, 4, 8])), int(rng.integers(1, 9))
-        f0, d0, g0 = run(emu, x[None], nranks, nwarps, flags=1)
-        f1, d1, g1 = run(emu, x[None], nranks, nwarps, flags=1 | 4)
-        assert d1[0, 79] == 1.0
-        assert np.array_equal(f0, f1), (T, nranks, nwarps)
-        assert np.array_equal(d0[:, :79], d1[:, :79], equal_nan=True), (T, nranks, nwarps)
-        assert np.array_equal(g0, g1), (T, nranks, nwarps)

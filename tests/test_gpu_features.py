@@ -14,7 +14,7 @@ import torch
 
 from oracle import features_np as fx
 from oracle import synth
-from tests.gpu_util import close, need_gpu
+from tests.gpu_util import close, need_gpu, residual_is_fp16_noise
 
 pytestmark = pytest.mark.gpu
 
@@ -76,7 +76,7 @@ def test_cluster_sizes_agree_with_oracle(ana, cluster, T):
     close(det[0, 24:27], raw[24:27], what="rhythm")
     close(det[0, 27:31], q, what="quality")
     assert np.abs(mf[0] - fx.mfcc(x[0].astype(np.float64)).T).max() < 2e-3      # MFCC values reach ~170
-    assert det[0, 66] < 1e-6 and det[0, 67] < 1e-6               # STFT -> ISTFT residual: std, max
+    residual_is_fp16_noise(det[0], float(np.abs(x).max()))      # STFT -> ISTFT residual: std, max
     assert det[0, 72] == T                                       # every sample reconstructed exactly once
     from msa_b200 import _lib
     assert ana._lib.msa_features_f32(_lib.ptr(torch.zeros(1, 800000, device=ana.device)), 1, 800000, None,
@@ -101,11 +101,11 @@ def test_finite_layernorm_and_emotion_embedding(ana, golden_features):
     g = golden_features
     seeds = [int(s) for s in g["seeds"][:4]]
     x = np.stack([synth.pcm_to_f32(synth.segment_pcm(s)) for s in seeds])
-    feat, det, _ = _detail(ana, x, flags=2)                     # not strict: intensity 0 -> finite LayerNorm row
+    feat, det, _ = _detail(ana, x, flags=0)                     # not strict: intensity 0 -> finite LayerNorm row
     for i in range(4):
         close(det[i, 32:63], g["ln31_finite"][i], rel=1e-3, floor=2e-5, what="ln31")
     emo = synth.emotion_probs(5, 4)
-    feat, det, _ = _detail(ana, x, emo=emo, flags=2)
+    feat, det, _ = _detail(ana, x, emo=emo, flags=0)
     for i in range(4):
         close(feat[i], fx.audio_row31(x[i], emo[i], finite_intensity=True), rel=1e-3, floor=2e-5, what="row with emotion")
 
@@ -173,7 +173,8 @@ def test_full_size_batch_properties(ana):
     d = d1.cpu().numpy()
     assert np.all(np.abs(d[:, 8]) <= 1e-6) and np.all(np.isnan(d[:, 9])) and np.all(d[:, 23] == 1.0)
     assert np.all(d[:, 26] == np.float32(498 / 16000)) and np.all(d[:, 72] == 80000)
-    assert np.all(d[:, 66] < 1e-6)                                                   # perfect reconstruction everywhere
+    for i in range(d.shape[0]):                                                      # reconstruction everywhere (fp16 round trip)
+        residual_is_fp16_noise(d[i], 1.0)
     assert np.all((d[:, 27:31] >= 0) & (d[:, 27:31] <= 1))
     for i in idx:                                                                    # spot-check against the oracle
         x = synth.pcm_to_f32(pcm[i].cpu().numpy())
