@@ -136,7 +136,7 @@ struct GpuEnv {
     const u32* a = ag(0);
     const u32* b = bg(0);
     const u32 c0 = accumulate ? d[0] : 0u, c1 = accumulate ? d[1] : 0u;
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%9};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%9};"
                  : "=r"(d[0]), "=r"(d[1])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(c0), "r"(c1));
   }
@@ -151,7 +151,7 @@ struct GpuEnv {
   template <class D> __device__ __forceinline__ void movmt(D dg) {
     u32* d = dg(0);
     u32 o;
-    asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(o) : "r"(d[0]));
+    asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(o) : "r"(d[0]));
     d[0] = o;
   }
 

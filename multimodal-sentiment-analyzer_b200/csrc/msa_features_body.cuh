@@ -52,15 +52,19 @@ namespace msa {
 
 constexpr int kDetailStride = 96;
 constexpr int kRow512 = 33, kRow400 = 25;        // row strides (complex words) of the pass-A -> pass-B tiles
-constexpr int kFftHalf = 16 * kRow512;           // one FFT tile: 528 complex = 4224 bytes
-constexpr int kWarpBufBytes = 2 * kFftHalf * 8;  // two tiles per warp
+constexpr int kFftHalf = 16 * kRow512;           // spacing (complex words) of the two power-spectrum row pairs in a warp's buffer
 constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
 constexpr int kRedSlots = 16;
 constexpr int kK1Groups = 2;                     // load groups in flight per warp in the wave-statistics phase (160 floats of scratch each; 4 in flight measured no faster)
 constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
 constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (the largest MFCC use of a warp's buffer)
 // top_db candidates of one warp live behind the transpose tile: 198 entries of (frame << 7 | filter, dB)
-constexpr int kClampCap = (kWarpBufBytes - kShareBytes) / 8;
+constexpr int kClampCap = 176;
+// a warp's private buffer: MFCC FFT tiles (2 x 3200 B), power rows, the transpose tile + candidate list; the wave-statistics
+// scratch and the fp16 ring of the STFT-512 round trip (4096 B) reuse it in their own phases.  Sized so that the whole
+// layout of a 5 s segment stays below half an SM's shared memory (two CTAs per SM).
+constexpr int kWarpBufBytes = kShareBytes + kClampCap * 8;
+static_assert(kWarpBufBytes % 16 == 0 && kWarpBufBytes >= 2 * kFftHalf * 4 + 2 * kPowStride * 4 && kWarpBufBytes >= kRing * 2, "warp buffer");
 
 enum : int { kPartWave = 1, kPartMfcc = 2, kPartPitch = 4, kPartAll = 7 };
 enum : int { kFlagStrictNan = 1 };
@@ -219,7 +223,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   const FeatLayout lay = feat_layout(T, NR, NW);
   const InT* x = reinterpret_cast<const InT*>(P.wav) + (size_t)seg * T;
 
-  c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off) + env.warp * (2 * kFftHalf);   // this warp's two FFT tiles
+  c32* wbuf = reinterpret_cast<c32*>(smem + lay.buf_off + env.warp * kWarpBufBytes);   // this warp's private buffer
   double* wred = reinterpret_cast<double*>(smem + lay.wred_off);
   float* mfl = reinterpret_cast<float*>(smem + lay.mfl_off);
   float* atoms = reinterpret_cast<float*>(smem + lay.atoms_off);

@@ -137,8 +137,11 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         env.mma(MSA_R(yre[li_][j]), MSA_R(a1[li_][0]), MSA_R(bre[li_][j]), false);
-        env.mma(MSA_R(yre[li_][j]), MSA_R(a1[li_][2]), MSA_R(bim[li_][j]), true);
         env.mma(MSA_R(yim[li_][j]), MSA_R(a1[li_][0]), MSA_R(bim[li_][j]), false);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        env.mma(MSA_R(yre[li_][j]), MSA_R(a1[li_][2]), MSA_R(bim[li_][j]), true);
         env.mma(MSA_R(yim[li_][j]), MSA_R(a1[li_][1]), MSA_R(bre[li_][j]), true);
       }
       // ---- twiddle W512^(k1 n2) = tc - i ts; the negated real part feeds the "- Y're sin" products of stage 2
@@ -159,22 +162,31 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
 
       // ---- stage 2: Z = Y' W32 / 16 (W32 = cos - i sin): K = (re | im) x n2 = 4 steps of 16, N = k2 tiles m
       u32 zre[S][4][2], zim[S][4][2], nzim[S][4][2];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        u32 c0[S][2], c1[S][2], s0[S][2], s1[S][2];
+      // four rounds (cos | sin) x (n2 < 16 | n2 >= 16) of eight INDEPENDENT products: a warp never waits for its own accumulator
+      static_for<0, 4>([&](auto rc) {
+        constexpr int R = decltype(rc)::value;
+        u32 b[S][4][2];
         env.lanes([&](int lane, int li) {
-          env.lds2(c0[li], pt->cs[m][lane]); env.lds2(c1[li], pt->cs[4 + m][lane]);
-          env.lds2(s0[li], pt->cs[8 + m][lane]); env.lds2(s1[li], pt->cs[12 + m][lane]);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) env.lds2(b[li][m], pt->cs[4 * R + m][lane]);
         });
-        env.mma(MSA_R(zre[li_][m]), MSA_R(&yre[li_][0][0]), MSA_R(c0[li_]), false);
-        env.mma(MSA_R(zre[li_][m]), MSA_R(&yre[li_][2][0]), MSA_R(c1[li_]), true);
-        env.mma(MSA_R(zre[li_][m]), MSA_R(&yim[li_][0][0]), MSA_R(s0[li_]), true);
-        env.mma(MSA_R(zre[li_][m]), MSA_R(&yim[li_][2][0]), MSA_R(s1[li_]), true);
-        env.mma(MSA_R(zim[li_][m]), MSA_R(&yim[li_][0][0]), MSA_R(c0[li_]), false);
-        env.mma(MSA_R(zim[li_][m]), MSA_R(&yim[li_][2][0]), MSA_R(c1[li_]), true);
-        env.mma(MSA_R(zim[li_][m]), MSA_R(&nyre[li_][0][0]), MSA_R(s0[li_]), true);
-        env.mma(MSA_R(zim[li_][m]), MSA_R(&nyre[li_][2][0]), MSA_R(s1[li_]), true);
-      }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (R == 0) {
+            env.mma(MSA_R(zre[li_][m]), MSA_R(&yre[li_][0][0]), MSA_R(b[li_][m]), false);
+            env.mma(MSA_R(zim[li_][m]), MSA_R(&yim[li_][0][0]), MSA_R(b[li_][m]), false);
+          } else if (R == 1) {
+            env.mma(MSA_R(zre[li_][m]), MSA_R(&yre[li_][2][0]), MSA_R(b[li_][m]), true);
+            env.mma(MSA_R(zim[li_][m]), MSA_R(&yim[li_][2][0]), MSA_R(b[li_][m]), true);
+          } else if (R == 2) {
+            env.mma(MSA_R(zre[li_][m]), MSA_R(&yim[li_][0][0]), MSA_R(b[li_][m]), true);
+            env.mma(MSA_R(zim[li_][m]), MSA_R(&nyre[li_][0][0]), MSA_R(b[li_][m]), true);
+          } else {
+            env.mma(MSA_R(zre[li_][m]), MSA_R(&yim[li_][2][0]), MSA_R(b[li_][m]), true);
+            env.mma(MSA_R(zim[li_][m]), MSA_R(&nyre[li_][2][0]), MSA_R(b[li_][m]), true);
+          }
+        }
+      });
       env.lanes([&](int lane, int li) {
         (void)lane;
 #pragma unroll
@@ -183,22 +195,30 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
 
       // ---- stage 3: O = Z conj(W32) / 16: K = (re | im) x k2, N = n2 tiles j
       u32 ore[S][4][2], oim[S][4][2];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        u32 c0[S][2], c1[S][2], s0[S][2], s1[S][2];
+      static_for<0, 4>([&](auto rc) {
+        constexpr int R = decltype(rc)::value;
+        u32 b[S][4][2];
         env.lanes([&](int lane, int li) {
-          env.lds2(c0[li], pt->cs[j][lane]); env.lds2(c1[li], pt->cs[4 + j][lane]);
-          env.lds2(s0[li], pt->cs[8 + j][lane]); env.lds2(s1[li], pt->cs[12 + j][lane]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) env.lds2(b[li][j], pt->cs[4 * R + j][lane]);
         });
-        env.mma(MSA_R(ore[li_][j]), MSA_R(&zre[li_][0][0]), MSA_R(c0[li_]), false);
-        env.mma(MSA_R(ore[li_][j]), MSA_R(&zre[li_][2][0]), MSA_R(c1[li_]), true);
-        env.mma(MSA_R(ore[li_][j]), MSA_R(&nzim[li_][0][0]), MSA_R(s0[li_]), true);
-        env.mma(MSA_R(ore[li_][j]), MSA_R(&nzim[li_][2][0]), MSA_R(s1[li_]), true);
-        env.mma(MSA_R(oim[li_][j]), MSA_R(&zim[li_][0][0]), MSA_R(c0[li_]), false);
-        env.mma(MSA_R(oim[li_][j]), MSA_R(&zim[li_][2][0]), MSA_R(c1[li_]), true);
-        env.mma(MSA_R(oim[li_][j]), MSA_R(&zre[li_][0][0]), MSA_R(s0[li_]), true);
-        env.mma(MSA_R(oim[li_][j]), MSA_R(&zre[li_][2][0]), MSA_R(s1[li_]), true);
-      }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (R == 0) {
+            env.mma(MSA_R(ore[li_][j]), MSA_R(&zre[li_][0][0]), MSA_R(b[li_][j]), false);
+            env.mma(MSA_R(oim[li_][j]), MSA_R(&zim[li_][0][0]), MSA_R(b[li_][j]), false);
+          } else if (R == 1) {
+            env.mma(MSA_R(ore[li_][j]), MSA_R(&zre[li_][2][0]), MSA_R(b[li_][j]), true);
+            env.mma(MSA_R(oim[li_][j]), MSA_R(&zim[li_][2][0]), MSA_R(b[li_][j]), true);
+          } else if (R == 2) {
+            env.mma(MSA_R(ore[li_][j]), MSA_R(&nzim[li_][0][0]), MSA_R(b[li_][j]), true);
+            env.mma(MSA_R(oim[li_][j]), MSA_R(&zre[li_][0][0]), MSA_R(b[li_][j]), true);
+          } else {
+            env.mma(MSA_R(ore[li_][j]), MSA_R(&nzim[li_][2][0]), MSA_R(b[li_][j]), true);
+            env.mma(MSA_R(oim[li_][j]), MSA_R(&zre[li_][2][0]), MSA_R(b[li_][j]), true);
+          }
+        }
+      });
       // ---- conjugate twiddle, then every 8 x 8 tile is transposed into the B-operand layout of stage 4
       env.lanes([&](int lane, int li) {
         (void)lane;
@@ -236,8 +256,11 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         env.mma(MSA_R(ye[li_][j]), MSA_R(vre_e[li_]), MSA_R(ore[li_][j]), false);
-        env.mma(MSA_R(ye[li_][j]), MSA_R(nvim_e[li_]), MSA_R(oim[li_][j]), true);
         env.mma(MSA_R(yo[li_][j]), MSA_R(vre_o[li_]), MSA_R(oim[li_][j]), false);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        env.mma(MSA_R(ye[li_][j]), MSA_R(nvim_e[li_]), MSA_R(oim[li_][j]), true);
         env.mma(MSA_R(yo[li_][j]), MSA_R(vim_o[li_]), MSA_R(ore[li_][j]), true);
       }
 
