@@ -99,8 +99,28 @@ def current_stream_ptr(device=None):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def normalize_device(device):
+    """torch.device with an explicit index: torch.device("cuda") != torch.device("cuda", 0), so every comparison and
+    every ``with torch.cuda.device(...)`` in this package goes through the normalised form."""
+    import torch
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.type == "cuda" and dev.index is None and torch.cuda.is_available():
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
 def require_cuda(device):
     import torch
     if not torch.cuda.is_available():
         raise MsaError("msa_b200 needs a CUDA device (B200, sm_100a); there is no CPU path.")
-    return torch.device(device if device is not None else "cuda")
+    dev = normalize_device(device)
+    if dev.type != "cuda":
+        raise MsaError(f"msa_b200 needs a CUDA device, got {dev}; there is no CPU path.")
+    return dev
+
+
+def on_device(device):
+    """Context manager: make `device` the current CUDA device for the C-ABI calls inside (the library launches on the
+    current device and builds its constant tables per device)."""
+    import torch
+    return torch.cuda.device(device)

@@ -48,6 +48,7 @@ class AudioAnalyzer:
         self.emotion_embedding: Optional[torch.Tensor] = None   # injected [1, 8] output of the out-of-scope SER model
         self._lib = _lib.lib()
         self._ws: Optional[torch.Tensor] = None
+        self.buffers_generation = 0     # bumped when the scratch table is reallocated (captured graphs hold its address)
         logger.info("AudioAnalyzer (msa_b200, sm_100a) on %s, sample_rate %d", self.device, sample_rate)
 
     # ------------------------------------------------------------------ kernel entry
@@ -63,8 +64,9 @@ class AudioAnalyzer:
         mfcc = torch.empty(B, T // 200 + 1, 13, device=self.device, dtype=torch.float32) if want_mfcc else None
         fn = self._lib.msa_features_ws_s16 if waves.dtype == torch.int16 else self._lib.msa_features_ws_f32
         ws = self._workspace(B, T)
-        rc = fn(_lib.ptr(waves), B, T, _lib.ptr(emo8), _lib.ptr(feat), _lib.ptr(detail), _lib.ptr(mfcc), self._flags(), parts, 0,
-                _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
+        with _lib.on_device(self.device):
+            rc = fn(_lib.ptr(waves), B, T, _lib.ptr(emo8), _lib.ptr(feat), _lib.ptr(detail), _lib.ptr(mfcc), self._flags(), parts, 0,
+                    _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
         _lib.check(rc, "msa_features")
         return feat, detail, mfcc
 
@@ -72,7 +74,9 @@ class AudioAnalyzer:
         """Grow-only scratch table for the top_db clamp of pause-heavy segments (msa_features_workspace_bytes)."""
         need = self._lib.msa_features_workspace_bytes(B, T)
         if self._ws is None or self._ws.numel() < need:
+            self._ws = None
             self._ws = torch.empty(max(int(need), 1), dtype=torch.uint8, device=self.device)
+            self.buffers_generation += 1
         return self._ws
 
     def _mono(self, waveform: torch.Tensor) -> torch.Tensor:
@@ -107,17 +111,21 @@ class AudioAnalyzer:
         feat, detail, _ = self._run(w, self._emo(w.shape[0], emotion_probs), _lib.PART_ALL)
         return (feat, detail) if return_detail else feat
 
-    def analyze_into(self, waveforms: torch.Tensor, out_rows: torch.Tensor, emotion_probs: Optional[torch.Tensor] = None) -> None:
+    def analyze_into(self, waveforms: torch.Tensor, out_rows: torch.Tensor, emotion_probs: Optional[torch.Tensor] = None,
+                     workspace: Optional[torch.Tensor] = None) -> None:
         """``analyze_batch`` writing the [B, 31] rows into a caller-owned contiguous buffer (no detail record,
-        no allocation): the chunked host-buffer pipeline fills one row table slice by slice."""
+        no allocation): the chunked host-buffer pipeline fills one row table slice by slice.  ``workspace``: a
+        caller-owned scratch table of ``msa_features_workspace_bytes(B, T)`` bytes (a CUDA-graph capture must not depend
+        on this object's grow-only table, whose address changes when a larger batch comes along)."""
         B, T = waveforms.shape
         if (not waveforms.is_contiguous() or not out_rows.is_contiguous() or out_rows.shape != (B, 31)
                 or out_rows.dtype != torch.float32 or waveforms.dtype not in (torch.int16, torch.float32)):
             raise ValueError("analyze_into needs contiguous [B, T] int16/fp32 waves and a contiguous fp32 [B, 31] output")
         fn = self._lib.msa_features_ws_s16 if waveforms.dtype == torch.int16 else self._lib.msa_features_ws_f32
-        ws = self._workspace(B, T)
-        rc = fn(_lib.ptr(waveforms), B, T, _lib.ptr(self._emo(B, emotion_probs)), _lib.ptr(out_rows), None, None, self._flags(),
-                _lib.PART_ALL, 0, _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
+        ws = workspace if workspace is not None else self._workspace(B, T)
+        with _lib.on_device(self.device):
+            rc = fn(_lib.ptr(waveforms), B, T, _lib.ptr(self._emo(B, emotion_probs)), _lib.ptr(out_rows), None, None, self._flags(),
+                    _lib.PART_ALL, 0, _lib.ptr(ws), ws.numel(), _lib.current_stream_ptr(self.device))
         _lib.check(rc, "msa_features")
 
     def track_pitch(self, waveforms: torch.Tensor, with_voicing: bool = True):
@@ -135,8 +143,9 @@ class AudioAnalyzer:
         f0 = torch.empty(B, lib.msa_pitch_outputs(T), device=self.device, dtype=torch.float32)
         voiced = torch.empty(B, lib.msa_voiced_frames(T), device=self.device, dtype=torch.int32) if with_voicing else None
         fn = lib.msa_pitch_track_s16 if w.dtype == torch.int16 else lib.msa_pitch_track_f32
-        _lib.check(fn(_lib.ptr(w), B, T, _lib.ptr(lags), _lib.ptr(f0), _lib.ptr(voiced), _lib.current_stream_ptr(self.device)),
-                   "msa_pitch_track")
+        with _lib.on_device(self.device):
+            _lib.check(fn(_lib.ptr(w), B, T, _lib.ptr(lags), _lib.ptr(f0), _lib.ptr(voiced), _lib.current_stream_ptr(self.device)),
+                       "msa_pitch_track")
         return {"f0": f0, "lags": lags, "voiced": voiced}
 
     # ------------------------------------------------------------------ reference API
@@ -159,8 +168,9 @@ class AudioAnalyzer:
                 emotion_probs=ln[0:8].reshape(1, 8).clone(), pitch=ln[8:9].reshape(1, 1).clone(),
                 intensity=ln[9:10].reshape(1, 1).clone(), timbre=ln[10:23].reshape(1, 13).clone(),
                 speech_rate=ln[23:24].reshape(1, 1).clone(), rhythm=ln[24:27].reshape(1, 3).clone(),
-                audio_quality=_pyfloat(q[0]), signal_noise_ratio=_pyfloat(q[1]), clarity=_pyfloat(q[2]),
-                consistency=_pyfloat(q[3]))
+                audio_quality=q[0], signal_noise_ratio=q[1], clarity=q[2], consistency=q[3])
+        except _lib.MsaError:
+            raise               # a missing library, a wrong device or a failed launch is not a data error: fail loudly
         except Exception as e:                                                        # noqa: BLE001 - reference convention
             logger.error("audio analysis failed: %s", e, exc_info=True)
             return self._get_default_analysis(speaker_id)
@@ -183,6 +193,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:175-188 -> [1, 1]."""
         try:
             return self._feature(waveform, _lib.PART_PITCH, slice(8, 9), (1, 1), 257)
+        except _lib.MsaError:
+            raise
         except Exception as e:  # noqa: BLE001
             print(f"Erro na análise de pitch: {e}")
             return torch.zeros(1, 1, device=self.device)
@@ -191,6 +203,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:190-201 -> [1, 1] (NaN for mono in strict mode)."""
         try:
             return self._feature(waveform, _lib.PART_WAVE, slice(9, 10), (1, 1), 1)
+        except _lib.MsaError:
+            raise
         except Exception as e:  # noqa: BLE001
             print(f"Erro na análise de intensidade: {e}")
             return torch.zeros(1, 1, device=self.device)
@@ -199,6 +213,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:203-217 -> [1, 13]."""
         try:
             return self._feature(waveform, _lib.PART_MFCC, slice(10, 23), (1, 13), 201)
+        except _lib.MsaError:
+            raise
         except Exception as e:  # noqa: BLE001
             print(f"Erro na análise de timbre: {e}")
             return torch.zeros(1, 13, device=self.device)
@@ -207,6 +223,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:219-233 -> [1, 1]."""
         try:
             return self._feature(waveform, _lib.PART_WAVE, slice(23, 24), (1, 1), 1)
+        except _lib.MsaError:
+            raise
         except Exception as e:  # noqa: BLE001
             print(f"Erro na análise de velocidade: {e}")
             return torch.zeros(1, 1, device=self.device)
@@ -215,6 +233,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:235-263 -> [1, 3]; T < 400 makes the reference's unfold raise -> zeros."""
         try:
             return self._feature(waveform, _lib.PART_WAVE, slice(24, 27), (1, 3), 400)
+        except _lib.MsaError:
+            raise
         except Exception as e:  # noqa: BLE001
             print(f"Erro na análise de ritmo: {e}")
             return torch.zeros(1, 3, device=self.device)
@@ -224,7 +244,7 @@ class AudioAnalyzer:
         if w.shape[1] < min_len:
             raise ValueError("too short")
         _, detail, _ = self._run(w, None, parts)
-        return _pyfloat(detail[0, 27 + idx].item())
+        return detail[0, 27 + idx].item()
 
     def _calculate_audio_quality(self, waveform: torch.Tensor) -> float:
         """audio_analyzer.py:265-276: 0.4 snr + 0.3 clarity + 0.3 consistency; a term whose own
@@ -232,6 +252,8 @@ class AudioAnalyzer:
         kernel reproduces per term."""
         try:
             return self._quality(waveform, _lib.PART_WAVE | _lib.PART_MFCC, 0, 1)
+        except _lib.MsaError:
+            raise
         except Exception:  # noqa: BLE001
             return 0.0
 
@@ -239,6 +261,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:278-293; int(0.05*T) == 0 makes torch.cat raise -> 0.0."""
         try:
             return self._quality(waveform, _lib.PART_WAVE, 1, 20)
+        except _lib.MsaError:
+            raise
         except Exception:  # noqa: BLE001
             return 0.0
 
@@ -246,6 +270,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:295-311."""
         try:
             return self._quality(waveform, _lib.PART_MFCC, 2, 201)
+        except _lib.MsaError:
+            raise
         except Exception:  # noqa: BLE001
             return 0.0
 
@@ -253,6 +279,8 @@ class AudioAnalyzer:
         """audio_analyzer.py:313-329; T < 1600 makes unfold raise -> 0.0."""
         try:
             return self._quality(waveform, _lib.PART_WAVE, 3, 1600)
+        except _lib.MsaError:
+            raise
         except Exception:  # noqa: BLE001
             return 0.0
 
@@ -262,11 +290,6 @@ class AudioAnalyzer:
         return AudioAnalysis(speaker_id=speaker_id, emotion_probs=torch.ones(1, 8, device=self.device) / 8, pitch=z(1),
                              intensity=z(1), timbre=z(13), speech_rate=z(1), rhythm=z(3), audio_quality=0.0,
                              signal_noise_ratio=0.0, clarity=0.0, consistency=0.0)
-
-
-def _pyfloat(v: float):
-    """The reference's clamp helpers return python ints 0 / 1 at the rails (min(max(x, 0), 1))."""
-    return v
 
 
 def _read_wav(path: str):

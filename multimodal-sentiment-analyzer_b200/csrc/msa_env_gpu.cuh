@@ -13,6 +13,7 @@ namespace cg = cooperative_groups;
 struct GpuEnv {
   static constexpr int kStates = 1;
   int tid, nthreads, lane, warp, nwarps, rank, nranks, cluster_id;
+  bool mfcc_first;          // phase order of this CTA (see features_cta)
 
   template <class F> __device__ __forceinline__ void lanes(F&& f) { f(lane, 0); }
   __device__ __forceinline__ void sync() { __syncthreads(); }

@@ -22,6 +22,10 @@ __global__ void __launch_bounds__(kFeatThreads, 2) features_kernel(const FeatPar
   env.rank = (int)cluster.block_rank();
   env.nranks = (int)cluster.num_blocks();
   env.cluster_id = blockIdx.x / env.nranks;
+  // CTAs are placed round-robin over the SMs, two per SM: CTA i and CTA i + num_sms share one, and a CTA that finishes is
+  // replaced by one launched 2 * num_sms later.  Alternating the phase order every num_sms CTAs keeps the pair on an SM
+  // complementary (one on the tensor pipe, one on the FMA pipe).
+  env.mfcc_first = ((blockIdx.x / P.num_sms) & 1) != 0;
   features_cta<GpuEnv, InT>(env, P, smem);
 }
 
@@ -50,6 +54,19 @@ static int get_tables(const FeatureTables** out) {
 
 int feat_threads() { return kFeatThreads; }
 
+// SMs of the current device (read once per device; 148 on B200)
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 // Smallest cluster whose per-CTA shared-memory layout lets two CTAs share an SM, else the smallest that
 // fits at all (the per-segment MFCC tile and the energy atoms are split over the ranks; everything else
 // is per warp).
@@ -70,7 +87,7 @@ int features_cluster_size(int T) {
 static int auto_cluster_size(int B, int T) {
   int c = features_cluster_size(T);
   if (c == 0) return 0;
-  while (c < 8 && (long long)B * c * 2 <= 2 * kNumSms) c *= 2;      // up to two CTAs per SM
+  while (c < 8 && (long long)B * c * 2 <= 2 * sm_count()) c *= 2;      // up to two CTAs per SM
   return c;
 }
 
@@ -116,6 +133,7 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
   P.flags = flags;
+  P.num_sms = sm_count();
   P.parts = parts;
   const int threads = feat_threads();
   const FeatLayout lay = feat_layout(T, c, threads / 32);

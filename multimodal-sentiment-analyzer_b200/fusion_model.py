@@ -40,7 +40,7 @@ class AdvancedFusionModel(nn.Module):
         super().__init__()
         if (face_dim, audio_dim, text_dim, hidden_dim, output_dim) != (27, 31, 783, 1024, 7):
             raise ValueError("the sm_100a kernels are specialised for the reference's dimensions 27/31/783/1024/7")
-        self.device = device if device is not None else "cuda"
+        self.device = _lib.normalize_device(device)
         self.dropout = dropout
         self.audio_dim, self.text_dim, self.face_dim = audio_dim, text_dim, face_dim
         self.hidden_dim, self.output_dim = hidden_dim, output_dim
@@ -72,9 +72,17 @@ class AdvancedFusionModel(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self._packed_key = None
         self._workspace: Optional[torch.Tensor] = None
+        # bumped whenever _packed or _workspace is (re)allocated: captured CUDA graphs hold their raw addresses
+        # (StreamingWindow drops its graphs when this changes)
+        self.buffers_generation = 0
+        # load_state_dict invalidates the packed copy at once (the streaming path does not re-derive the parameter
+        # key on every hop; the batch path does)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: setattr(module, "_packed_key", None))
 
     # ------------------------------------------------------------------ device weights
     def _param_key(self):
+        # (address, autograd version) of every parameter: catches load_state_dict, optimiser steps and in-place ops.
+        # Writes through ``p.data`` do not bump the version: call repack() after those.
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def repack(self) -> None:
@@ -95,7 +103,10 @@ class AdvancedFusionModel(nn.Module):
             arr[i] = t.data_ptr()
         if self._packed is None or self._packed.device != dev:
             self._packed = torch.empty(l.msa_fusion_packed_bytes(), dtype=torch.uint8, device=dev)
-        _lib.check(l.msa_fusion_pack(arr, _lib.ptr(self._packed), _lib.current_stream_ptr(dev)), "msa_fusion_pack")
+            self.buffers_generation += 1
+        # repacked IN PLACE: the blob keeps its address, so graphs captured earlier read the new weights
+        with _lib.on_device(dev):
+            _lib.check(l.msa_fusion_pack(arr, _lib.ptr(self._packed), _lib.current_stream_ptr(dev)), "msa_fusion_pack")
         self._packed_key = self._param_key()
 
     def _ensure_packed(self):
@@ -105,7 +116,9 @@ class AdvancedFusionModel(nn.Module):
     def _ws(self, B: int, dev) -> torch.Tensor:
         need = _lib.lib().msa_fusion_workspace_bytes(B)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = None                                 # release the old block before taking the larger one
             self._workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+            self.buffers_generation += 1
         return self._workspace
 
     # ------------------------------------------------------------------ fused paths
@@ -124,8 +137,9 @@ class AdvancedFusionModel(nn.Module):
         logits = torch.empty(B, self.output_dim, device=dev, dtype=torch.float32)
         amax = torch.empty(B, device=dev, dtype=torch.int32) if want_argmax else None
         ws = self._ws(B, dev)
-        rc = _lib.lib().msa_fusion_forward(_lib.ptr(f), _lib.ptr(a), _lib.ptr(t), B, _lib.ptr(self._packed), _lib.ptr(ws),
-                                           ws.numel(), _lib.ptr(logits), _lib.ptr(amax), _lib.current_stream_ptr(dev))
+        with _lib.on_device(dev):
+            rc = _lib.lib().msa_fusion_forward(_lib.ptr(f), _lib.ptr(a), _lib.ptr(t), B, _lib.ptr(self._packed), _lib.ptr(ws),
+                                               ws.numel(), _lib.ptr(logits), _lib.ptr(amax), _lib.current_stream_ptr(dev))
         _lib.check(rc, "msa_fusion_forward")
         logits = logits.reshape(*lead, self.output_dim)
         return (logits, amax) if want_argmax else logits
@@ -134,13 +148,24 @@ class AdvancedFusionModel(nn.Module):
                      argmax_out: Optional[torch.Tensor]) -> None:
         """Allocation-free forward for CUDA-graph capture and tight loops: contiguous fp32 device inputs
         [B, 27] / [B, 31] / [B, 783] or None, outputs written into caller-owned [B, 7] fp32 and [B] int32.
-        Weights must already be packed (call once outside the capture)."""
+        Weights must already be packed and the workspace sized (``prepare(B)`` once outside the capture): inside a
+        capture nothing may be allocated, so a missing or too small buffer is an error here."""
         dev = self.device
         B = face.shape[0]
-        ws = self._ws(B, dev)
+        need = _lib.lib().msa_fusion_workspace_bytes(B)
+        if self._packed is None or self._workspace is None or self._workspace.numel() < need:
+            raise _lib.MsaError("forward_into: call prepare(B) first (weights packed, workspace sized)")
+        ws = self._workspace
         rc = _lib.lib().msa_fusion_forward(_lib.ptr(face), _lib.ptr(audio), _lib.ptr(text), B, _lib.ptr(self._packed), _lib.ptr(ws),
                                            ws.numel(), _lib.ptr(logits_out), _lib.ptr(argmax_out), _lib.current_stream_ptr(dev))
         _lib.check(rc, "msa_fusion_forward")
+
+    def prepare(self, B: int) -> None:
+        """Pack the weights and size the workspace for batches of up to B rows (allocation happens here, never in
+        ``forward_into``)."""
+        dev = _lib.require_cuda(self.device)
+        self._ensure_packed()
+        self._ws(B, dev)
 
     def fused_with_argmax(self, face, audio, text=None):
         """Additive batched entry point: (logits [B,7], argmax [B] int32) in one call."""
@@ -151,7 +176,8 @@ class AdvancedFusionModel(nn.Module):
         fusion_model.py:94, and its consumers argmax them)."""
         x = logits.to(self.device).float().reshape(-1, 7).contiguous()
         out = torch.empty_like(x)
-        _lib.check(_lib.lib().msa_softmax7(_lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.current_stream_ptr(self.device)), "msa_softmax7")
+        with _lib.on_device(self.device):
+            _lib.check(_lib.lib().msa_softmax7(_lib.ptr(x), x.shape[0], _lib.ptr(out), _lib.current_stream_ptr(self.device)), "msa_softmax7")
         return out.reshape(logits.shape)
 
     # ------------------------------------------------------------------ reference API

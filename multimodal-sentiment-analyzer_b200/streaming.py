@@ -76,30 +76,47 @@ class StreamingWindow:
     def _static(self):
         if self._g is None:
             dev = self.device
+            lib = self.analyzer._lib
             self._g = {"stage": torch.empty(self.hop, dtype=torch.int16).pin_memory(),
+                       "face_h": torch.zeros(1, 27).pin_memory(), "text_h": torch.zeros(1, 783).pin_memory(),
                        "face": torch.zeros(1, 27, device=dev), "text": torch.zeros(1, 783, device=dev),
                        "row": torch.zeros(1, 31, device=dev), "logits": torch.zeros(1, 7, device=dev),
                        "amax": torch.zeros(1, dtype=torch.int32, device=dev),
                        "out": torch.zeros(8, dtype=torch.float32).pin_memory(),          # 7 logits + argmax (as float)
-                       "stream": torch.cuda.Stream(dev)}
+                       # the window's OWN scratch table for the top_db clamp: a captured graph must not point into the
+                       # analyzer's grow-only table, which is replaced when a larger batch comes along
+                       "ws": torch.empty(max(1, lib.msa_features_workspace_bytes(1, self.window)), dtype=torch.uint8, device=dev),
+                       "stream": torch.cuda.Stream(dev), "done": torch.cuda.Event(), "busy": False, "gen": None}
         return self._g
 
     def _device_hop(self, p: int, has_text: bool):
-        """The device work of one hop at ring position p, on the current stream, with static buffers only."""
+        """The device work of one hop at ring position p, on the current stream, with static buffers only: the three
+        uploads (16 KB of PCM, the face row, the text row), the mirror copy, the two kernels' launches and the 32-byte
+        read-back are ALL inside the captured graph, so a hop costs the host one graph launch."""
         g = self._g
         self.ring[p:p + self.hop].copy_(g["stage"], non_blocking=True)
         self.ring[p + self.window:p + self.window + self.hop].copy_(self.ring[p:p + self.hop])
+        g["face"].copy_(g["face_h"], non_blocking=True)
+        if has_text:
+            g["text"].copy_(g["text_h"], non_blocking=True)
         nxt = (p + self.hop) % self.window
-        self.analyzer.analyze_into(self.ring[nxt:nxt + self.window][None, :], g["row"])
+        self.analyzer.analyze_into(self.ring[nxt:nxt + self.window][None, :], g["row"], workspace=g["ws"])
         self.fusion.forward_into(g["face"], g["row"], g["text"] if has_text else None, g["logits"], g["amax"])
         g["out"][:7].copy_(g["logits"][0], non_blocking=True)
         g["out"][7:8].copy_(g["amax"].float(), non_blocking=True)
 
     def _graph_for(self, p: int, has_text: bool):
+        g = self._static()
+        f = self.fusion
+        if f._packed is None or f._packed_key is None or f._workspace is None:
+            f.prepare(1)                                           # first hop, or load_state_dict since the last one
+        gen = f.buffers_generation
+        if g["gen"] != gen:                                        # the fusion model's packed blob or workspace moved:
+            self._graphs.clear()                                   # graphs captured before hold stale addresses
+            g["gen"] = gen
         key = (p, has_text)
         gr = self._graphs.get(key)
         if gr is None:
-            g = self._static()
             s = g["stream"]
             s.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(s):
@@ -117,20 +134,22 @@ class StreamingWindow:
         """chunk_pcm: [hop] int16 on the host.  Returns None until the window is full, then the dict of
         streaming_processor.py:302-320: {"fused_emotion": logits [7], "argmax": int, "audio_row": [31]}.
         On the graph path the results live in static buffers that the next push overwrites, and
-        ``result["host"]`` is a pinned [8] tensor (7 logits, argmax) valid after a stream synchronise."""
+        ``result["host"]`` is a pinned [8] tensor (7 logits, argmax) valid after ``result["done"].synchronize()``
+        (an event recorded behind the hop's read-back: waiting on it is cheaper than synchronising the stream)."""
         if not self.use_graph or (self.n_pushed + 1) * self.hop < self.window:
             return self._push_eager(chunk_pcm, face, text)
         g = self._static()
-        self.fusion._ensure_packed()
-        cur = torch.cuda.current_stream(self.device)
-        cur.synchronize() if self._g.get("busy") else None       # the previous replay has consumed the staging buffer
-        g["stage"].copy_(chunk_pcm.reshape(-1))
-        g["face"].copy_(face.reshape(1, -1), non_blocking=True)
+        if g["busy"]:
+            g["done"].synchronize()                                # the previous replay has consumed the staging buffers
+        g["stage"].copy_(chunk_pcm.reshape(-1))                    # host -> pinned (a pinned chunk costs a memcpy of 16 KB)
+        g["face_h"].copy_(face.reshape(1, -1))
         if text is not None:
-            g["text"].copy_(text.reshape(1, -1), non_blocking=True)
+            g["text_h"].copy_(text.reshape(1, -1))
         p = self.pos
         self._graph_for(p, text is not None).replay()
+        g["done"].record(torch.cuda.current_stream(self.device))
         g["busy"] = True
         self.pos = (p + self.hop) % self.window
         self.n_pushed += 1
-        return {"fused_emotion": g["logits"][0], "argmax": g["amax"][0], "audio_row": g["row"][0], "host": g["out"]}
+        return {"fused_emotion": g["logits"][0], "argmax": g["amax"][0], "audio_row": g["row"][0], "host": g["out"],
+                "done": g["done"]}
