@@ -37,17 +37,21 @@ if ROOT not in sys.path:
 SEG_SAMPLES = 80000
 SEG_SECONDS = 5.0
 ALGO_BYTES_PER_SEGMENT = 80000 * 4 + 31 * 4          # waveform read once + 31-float row written
+FP32_FLOP_PER_SEGMENT = 18.5e6                        # split-radix count of the path's FFTs
+FP32_PEAK_TFLOPS = 74.0                               # 148 SMs x 128 lanes x 2 x 1.965 GHz
 METRIC = "audio-sec/s (features+fusion)"
 UNIT = "audio-s/s"
 
 
-def measured_traffic(segments):
-    """DRAM bytes per launch of the feature kernel from the committed ncu --set full capture (same batch size)."""
-    p = os.path.join(ROOT, "profiles", "r1_features_traffic.json")
+def measured_traffic(segments, lib_version):
+    """DRAM bytes per launch of the feature kernel from the committed ncu --set full capture: only when that capture
+    was taken at this batch size from THIS build of the library (profiles/features_traffic.json is stamped with
+    msa_version(); a capture of another build gives null)."""
+    p = os.path.join(ROOT, "profiles", "features_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)
-        if int(d["segments"]) == int(segments):
+        if int(d["segments"]) == int(segments) and int(d["msa_version"]) == int(lib_version):
             return int(d["dram_bytes_read"]) + int(d["dram_bytes_write"])
     except Exception:  # noqa: BLE001
         pass
@@ -105,13 +109,36 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU arm
+def cpu_kind():
+    """"reference" when the reference's source tree is on this machine ($MSA_REFERENCE_DIR or /root/reference: the build
+    container), else "port" (the GPU box: the pinned torch port of the same calls)."""
+    from oracle import ref_runner
+    return "reference" if ref_runner.available() else "port"
+
+
 def cpu_port_throughput(budget_s: float, workers: int, segs_per_task: int = 2):
-    """audio-s/s of the reference port on host cores: (features + fusion) per segment."""
+    """audio-s/s of the reference (or its pinned port) on host cores: (features + fusion) per segment."""
     import numpy as np
     import torch
-    from oracle import synth, torch_port as tp
+    from oracle import ref_runner, synth, torch_port as tp
 
-    sd = tp.build_fusion(synth.fusion_state(4321, trained_like=True))
+    use_ref = ref_runner.available()
+    sd_np = synth.fusion_state(4321, trained_like=True)
+    sd = tp.build_fusion(sd_np)
+    work = ref_runner.worker if use_ref else tp._worker
+    fuse = (lambda f, a, t: ref_runner.fusion_forward(sd_np, f, a, t)) if use_ref else (lambda f, a, t: tp.fusion_forward(sd, f, a, t))
+    if workers <= 1 and use_ref:
+        ref_runner.worker((1234, 1))                                     # imports, first-call caches
+        t0 = time.perf_counter()
+        ref_runner.worker((1234, 1))
+        per = max((time.perf_counter() - t0) / 2.0, 1e-3)
+        n = int(min(4096, max(8, budget_s / per)))
+        rows, dt = ref_runner.worker((1234, n))
+        torch.set_num_threads(os.cpu_count() or 1)
+        t0 = time.perf_counter()
+        fuse(torch.from_numpy(synth.face_rows(1, n)), torch.from_numpy(rows), torch.from_numpy(synth.text_rows(3, n)))
+        dt += time.perf_counter() - t0
+        return n * SEG_SECONDS / dt, n, 1
     if workers <= 1:
         ana = tp.PortedAnalyzer()
         waves = [torch.from_numpy(synth.pcm_to_f32(synth.segment_pcm(1234 + i)))[None, :] for i in range(8)]
@@ -129,15 +156,15 @@ def cpu_port_throughput(budget_s: float, workers: int, segs_per_task: int = 2):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
-        probe = pool.map(tp._worker, [(1, 2)] * workers)              # warm-up + per-segment cost probe
+        probe = pool.map(work, [(1, 2)] * workers)                    # warm-up + per-segment cost probe
         per = max(max(dt for _, dt in probe) / 2.0, 1e-3)
         count = int(min(2048, max(4, budget_s / per)))
-        out = pool.map(tp._worker, [(5000 + i * count, count) for i in range(workers)], chunksize=1)
+        out = pool.map(work, [(5000 + i * count, count) for i in range(workers)], chunksize=1)
     a = torch.from_numpy(np.concatenate([r for r, _ in out]))
     n = a.shape[0]
     torch.set_num_threads(workers)
     t0 = time.perf_counter()
-    tp.fusion_forward(sd, torch.from_numpy(synth.face_rows(1, n)), a, torch.from_numpy(synth.text_rows(3, n)))
+    fuse(torch.from_numpy(synth.face_rows(1, n)), a, torch.from_numpy(synth.text_rows(3, n)))
     t_fus = time.perf_counter() - t0
     # the workers run concurrently: job time = slowest worker's compute + the batched fusion forward
     dt = max(d for _, d in out) + t_fus
@@ -165,8 +192,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "5 s 16 kHz mono segments, feature body of AudioAnalyzer.analyze + 3-modal fusion forward (BASELINE configs[1] shape), CPU",
                    "segments_per_step": n_total // max(1, args.steps)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n_total} segments over {args.steps} steps, {cores} processes x 1 torch thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                         "sample": f"{n_total} segments over {args.steps} steps, {cores} processes x 1 torch thread"
+                                   + (" (the reference's own source tree)" if cpu_kind() == "reference" else " (oracle/torch_port.py: the reference tree is not on this machine)")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -301,19 +329,23 @@ def run_native(args):
     if rank == 0 and world == 1 and not args.no_streaming:
         sw = msa_b200.StreamingWindow(ana, model, window=SEG_SAMPLES, hop=8000)
         chunks = pcm_host[:64].reshape(-1, 8000)
-        face1, text1 = face_dev[0], text_dev[0]
+        face1, text1 = face_host[0], text_host[0]                     # host rows: they ride in the hop's graph like the PCM chunk
         lat = []
         for i in range(args.stream_chunks + 20):
             t0 = time.perf_counter()
             out = sw.push(chunks[i % chunks.shape[0]], face1, text1)
-            torch.cuda.synchronize()
-            if out is not None:
-                logits_host = out["host"][:7] if "host" in out else out["fused_emotion"].cpu()     # pinned read-back
+            if out is not None and "done" in out:
+                out["done"].synchronize()                                # event behind the 32-byte read-back of this hop
+                logits_host = out["host"][:7]                            # pinned
+            else:
+                torch.cuda.synchronize()
+                if out is not None:
+                    logits_host = out["fused_emotion"].cpu()
             if i >= 20:
                 lat.append((time.perf_counter() - t0) * 1e3)
         lat.sort()
         stream = {"p50_ms": lat[len(lat) // 2], "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))], "chunks": len(lat),
-                  "window_s": 5.0, "hop_s": 0.5, "timing": "host perf_counter around StreamingWindow.push (one CUDA graph per hop: upload, feature kernel, fusion chain, logits read-back) + synchronize"}
+                  "window_s": 5.0, "hop_s": 0.5, "timing": "host perf_counter around StreamingWindow.push (one CUDA graph per hop: PCM/face/text upload, feature kernel, fusion chain, logits read-back) + wait on the hop's event"}
 
     # the reference's own per-segment call (BASELINE configs[0] shape): AudioAnalyzer.analyze(path, speaker) on a 5 s wav
     # file followed by the fusion forward on its row, host wall-clock per call (file read, upload, kernels, read-back)
@@ -340,6 +372,43 @@ def run_native(args):
             api = {"p50_ms": lat[len(lat) // 2], "calls": len(lat),
                    "what": "AudioAnalyzer.analyze(wav path) + row assembly + AdvancedFusionModel.forward + argmax, one 5 s segment"}
 
+    # ---- BASELINE configs[2]: one hour of audio = 720 tumbling 5 s segments, STRONG-scaled over the ranks (contiguous shards),
+    # one all_gather of the result rows, speaker aggregation on the gathered table (offline_processor.py:255-298)
+    hour = None
+    if not args.no_extra:
+        HS, NSPK = 720, 4
+        from msa_b200.pipeline import shard_range, unpack_rows
+        hb, he = shard_range(HS, world, rank)
+        h_pcm = torch.from_numpy(synth.fast_segments_pcm(900, HS)[hb:he]).to(dev)
+        h_face = torch.from_numpy(synth.face_rows(901, HS)[hb:he]).to(dev)
+        h_text = torch.from_numpy(synth.text_rows(902, HS)[hb:he]).to(dev)
+        spk = torch.from_numpy(np.random.default_rng(903).integers(0, NSPK, HS).astype(np.int32)).to(dev)
+        def hour_step():
+            table = pipe.run_sharded(h_pcm, h_face, h_text, HS, world, rank)
+            return msa_b200.aggregate_speakers(unpack_rows(table)["argmax"], spk, NSPK)
+        ms_hour = timed(hour_step, args.steps, args.warmup) / args.steps
+        hour = {"segments": HS, "audio_s": HS * SEG_SECONDS, "ms": ms_hour, "value": HS * SEG_SECONDS / (ms_hour / 1000.0), "unit": UNIT,
+                "scaling": "strong", "n_gpus": world, "segments_per_gpu": he - hb, "input": "int16 PCM resident in HBM",
+                "what": "features + 3-modal fusion per shard, one all_gather of [S/N, 40] rows, speaker aggregation (histogram, dominant label, 3-in-a-row patterns)"}
+        del h_pcm, h_face, h_text
+
+    # ---- BASELINE configs[3]: fusion forward only, batch 65,536, synthetic face / audio / text rows (rank 0's GPU at N = 1)
+    fus65 = None
+    if world == 1 and not args.no_extra:
+        FB = 65536
+        f_face = torch.from_numpy(synth.face_rows(910, FB)).to(dev)
+        f_audio = torch.from_numpy(synth.audio_rows(911, FB)).to(dev)
+        f_text = torch.from_numpy(synth.text_rows(912, FB)).to(dev)
+        def fus65_step():
+            model.fused_with_argmax(f_face, f_audio, f_text)
+        ms_f65 = timed(fus65_step, max(3, args.steps // 2), args.warmup) / max(3, args.steps // 2)
+        tpeak, tsrc = measured_tensor_peak()
+        algo = 9069568.0 * FB / (ms_f65 / 1000.0) / 1e12
+        fus65 = {"rows": FB, "ms": ms_f65, "rows_per_s": FB / (ms_f65 / 1000.0), "algorithmic_tflops": algo, "issued_bf16_tflops": 3.0 * algo,
+                 "peak": tpeak, "peak_source": tsrc + " (sustained dense bf16)", "frac": algo / tpeak, "frac_issued": 3.0 * algo / tpeak,
+                 "note": "algorithmic = 9,069,568 FLOP per row counted once; every product is three bf16 MMAs (split-bf16, fp32 accumulate)"}
+        del f_face, f_audio, f_text
+
     if rank == 0:
         audio_s = S * SEG_SECONDS * world
         value = audio_s * args.steps / (ms_total / 1000.0)
@@ -349,8 +418,9 @@ def run_native(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, n, threads = cpu_port_throughput(12.0, 1)
-            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"{n} segments, one process, {threads} torch intra-op threads (oracle/torch_port.py)"}
+            cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": cpu_kind(),
+                   "sample": f"{n} segments, one process, {threads} torch intra-op threads ("
+                             + ("the reference's own source tree)" if cpu_kind() == "reference" else "oracle/torch_port.py)")}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -359,9 +429,13 @@ def run_native(args):
                        "segments_per_gpu": S, "segment_samples": SEG_SAMPLES, "fusion": "3-modal, split-bf16 tcgen05, fp32 accumulate",
                        "l2": "inputs larger than L2 (328 MB fp32 per GPU vs 126 MB)", "parallelism": f"segments sharded x{world}, one all_gather of result rows"},
             "roofline": {"bound": "hbm", "kernel": "features_kernel<float>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic(S), "traffic_unit": "bytes per launch (ncu dram read+write)",
+                         "frac": achieved / peak, "traffic": measured_traffic(S, lib.msa_version()), "traffic_unit": "bytes per launch (ncu dram read+write; null unless profiles/features_traffic.json was captured from this build)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_SEGMENT * S, "peak_source": peak_src,
-                         "ms_per_launch": ms_feat, "note": "bound by fp32 arithmetic (register FFTs: ~58 FLOP per waveform byte vs a ridge of ~11), not by HBM: ncu FMA pipe 42 % busy, issue slots 46 %, see DESIGN.md 4.1"},
+                         "ms_per_launch": ms_feat, "msa_version": lib.msa_version(),
+                         "fp32": {"flop_per_segment": FP32_FLOP_PER_SEGMENT, "achieved_tflops": FP32_FLOP_PER_SEGMENT * S / (ms_feat / 1000.0) / 1e12,
+                                  "peak_tflops": FP32_PEAK_TFLOPS, "frac": FP32_FLOP_PER_SEGMENT * S / (ms_feat / 1000.0) / 1e12 / FP32_PEAK_TFLOPS,
+                                  "note": "split-radix FLOP count of the path's transforms (626 x 2 real 512-point + 401 real 400-point per segment) against the CUDA-core fp32 peak; the 512-point round trip now runs as fp16 matrix products on the tensor pipe, so this fraction only says how far the kernel is from an ideal fp32 FFT machine"},
+                         "note": "not HBM-bound: ~58 FLOP per waveform byte vs a ridge of ~11; see DESIGN.md 4.1 for what bounds it (latency at 16 warps per SM; shared-memory pipe ~57 %, tensor pipe ~27 %, issue slots ~45 %)"},
             "kernels_ms": {"features": ms_feat, "fusion_chain": ms_fus},
             "fusion_tensor": (lambda pk: {"bound": "tensor", "achieved": 9069568.0 * S / (ms_fus / 1000.0) / 1e12, "peak": pk[0], "unit": "TFLOP/s",
                                           "frac": 9069568.0 * S / (ms_fus / 1000.0) / 1e12 / pk[0], "peak_source": pk[1],
@@ -372,6 +446,8 @@ def run_native(args):
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(pcm_host.numel() * 2 + face_host.numel() * 4 + text_host.numel() * 4) * world,
                     "d2h_bytes_per_step": int(rows_host.numel() * 4) * world, "ms_per_step": ms_e2e / args.steps, "input": "int16 PCM from pinned host memory", "h2d_only_ms": ms_h2d,
                     "pipeline": f"SegmentPipeline.run_host: {args.chunk}-segment chunks, upload overlapped with compute"},
+            "hour_sharded": hour,
+            "fusion_only_65536": fus65,
             "stream_latency": stream,
             "reference_api_call": api,
             "gpu_launches": int(launches_timed),
@@ -392,6 +468,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=128, help="segments per upload chunk of the host-buffer (e2e) path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the hour_sharded (configs[2]) and fusion_only_65536 (configs[3]) measurements")
     ap.add_argument("--stream-chunks", type=int, default=500)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -13,7 +13,6 @@ namespace cg = cooperative_groups;
 struct GpuEnv {
   static constexpr int kStates = 1;
   int tid, nthreads, lane, warp, nwarps, rank, nranks, cluster_id;
-  bool mfcc_first;          // phase order of this CTA (see features_cta)
 
   template <class F> __device__ __forceinline__ void lanes(F&& f) { f(lane, 0); }
   __device__ __forceinline__ void sync() { __syncthreads(); }
@@ -116,11 +115,9 @@ struct GpuEnv {
       for (int i = 0; i < 16; ++i) v[i] = s16_to_f32((int)__ldg(p + i));
     }
   }
-  // 16 fp16 values (8 pairs) to 32-byte aligned shared memory
-  __device__ __forceinline__ void st16(uint16_t* dst, const u32* w) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  // 8 fp16 values (4 pairs) to 16-byte aligned shared memory
+  __device__ __forceinline__ void st8(uint16_t* dst, const u32* w) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ __forceinline__ u32 lds1(const u32* p) { return *p; }
   __device__ __forceinline__ void lds2(u32* d, const u32* p) {

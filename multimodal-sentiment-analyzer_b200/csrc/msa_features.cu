@@ -22,10 +22,6 @@ __global__ void __launch_bounds__(kFeatThreads, 2) features_kernel(const FeatPar
   env.rank = (int)cluster.block_rank();
   env.nranks = (int)cluster.num_blocks();
   env.cluster_id = blockIdx.x / env.nranks;
-  // CTAs are placed round-robin over the SMs, two per SM: CTA i and CTA i + num_sms share one, and a CTA that finishes is
-  // replaced by one launched 2 * num_sms later.  Alternating the phase order every num_sms CTAs keeps the pair on an SM
-  // complementary (one on the tensor pipe, one on the FMA pipe).
-  env.mfcc_first = ((blockIdx.x / P.num_sms) & 1) != 0;
   features_cta<GpuEnv, InT>(env, P, smem);
 }
 
@@ -133,7 +129,6 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   P.dbscratch = (workspace != nullptr && ws_bytes >= features_workspace_bytes(B, T)) ? static_cast<float*>(workspace) : nullptr;
   P.tab = tab;
   P.flags = flags;
-  P.num_sms = sm_count();
   P.parts = parts;
   const int threads = feat_threads();
   const FeatLayout lay = feat_layout(T, c, threads / 32);

@@ -83,7 +83,6 @@ struct FeatParams {
   const FeatureTables* tab;
   int flags;
   int parts;
-  int num_sms;           // SMs of the device (phase order of co-resident CTAs, see features_kernel)
 };
 
 struct Partials {
@@ -329,22 +328,16 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       e_noi[li] = acc;
     });
   }
-  // block totals of the wave statistics (the MFCC pass needs the atom maximum for its top_db candidate bound)
-  {
-    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
-      return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
-    });
-    if (env.tid == 0) {
-      part->e_total = rout[0]; part->e_noise = rout[1]; part->e_left = rout[2]; part->a_max = (float)rout[3];
-      part->n_atoms = n_atoms_local;
-    }
-  }
+  // per-warp totals go to scratch slots 4..7 WITHOUT a barrier: every warp moves on to its STFT-512 quads as
+  // soon as its own loads are in (this phase is pure load latency), and the block-level sums are formed together
+  // with the residual's, behind that phase's barrier
+  const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
+  reduce_warp_stage<4>(env, wred, 4, ops, [&](int li, int k) {
+    return k == 0 ? e_tot[li] : (k == 1 ? e_noi[li] : (k == 2 ? e_left[li] : (double)a_max[li]));
+  });
 
   // ---------------------------------------------------------------- K3: STFT-512 -> ISTFT residual (tensor cores)
-  // The round trip lives on the tensor pipe and the MFCC pass on the FMA pipe, so the two CTAs that share an SM run
-  // them in OPPOSITE order (env.mfcc_first): while one issues matrix products the other issues butterflies.
-  auto run_pitch = [&]() {
+  {
     double ps[S], pq[S], pn[S];
     float pmax[S];
     for (int i = 0; i < S; ++i) { ps[i] = pq[i] = pn[i] = 0.0; pmax[i] = 0.0f; }
@@ -354,17 +347,21 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       const int q_begin = (r * qper < nQ) ? r * qper : nQ;
       const int q_end = (q_begin + qper < nQ) ? q_begin + qper : nQ;
       // msa_pitch_tc.cuh: every warp owns a contiguous run of this rank's quads; its fp16 ring of the padded signal is
-      // the warp's own buffer (whatever the warp kept there before is dead: program order)
+      // the warp's own buffer (the wave-statistics scratch of the same warp is dead by now: program order)
       env.wsync();
       pitch_tc<Env, InT>(env, x, T, q_begin, q_end, reinterpret_cast<uint16_t*>(wbuf), &tb->pt, &P.tab->pr, ps, pq, pn, pmax);
     }
-    const int ops[4] = {kOpSum, kOpSum, kOpSum, kOpMax};
-    block_reduce<4>(env, wred, rout, ops, [&](int li, int k) {
+    const int ops[8] = {kOpSum, kOpSum, kOpSum, kOpMax, kOpSum, kOpSum, kOpSum, kOpMax};
+    reduce_warp_stage<4>(env, wred, 0, ops, [&](int li, int k) {
       return k == 0 ? ps[li] : (k == 1 ? pq[li] : (k == 2 ? pn[li] : (double)pmax[li]));
     });
-    if (env.tid == 0) { part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3]; }
-  };
-  const bool mfcc_first = env.mfcc_first && (P.parts & kPartMfcc);
+    reduce_block_stage<8>(env, wred, rout, ops);          // slots 4..7: the wave-statistics totals deposited above
+    if (env.tid == 0) {
+      part->p_sum = rout[0]; part->p_sumsq = rout[1]; part->p_n = rout[2]; part->p_max = (float)rout[3];
+      part->e_total = rout[4]; part->e_noise = rout[5]; part->e_left = rout[6]; part->a_max = (float)rout[7];
+      part->n_atoms = n_atoms_local;
+    }
+  }
 
   // ---------------------------------------------------------------- K2: STFT-400 -> power -> mel -> dB -> DCT shares
   const int nFm = T / kHopM + 1;
@@ -376,12 +373,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   const int mf_end = (4 * mq_end < nFm) ? 4 * mq_end : nFm;
   const int nfr = ((P.parts & kPartMfcc) && mf_end > mf_begin) ? mf_end - mf_begin : 0;
 
-  float cand = -3.0e38f, thr = -3.0e38f, gmax = -3.0e38f, gmin = 3.0e38f;
-  bool fix = false, slow = false;
-  // two phases in the order this CTA was given: the round trip (one call site: the code exists once) and the MFCC pass
-#pragma unroll 1
-  for (int phase = 0; phase < 2; ++phase) {
-  if ((phase == 1) == mfcc_first) { run_pitch(); continue; }
   // MFCC passes over this rank's quads.  Pass 0: no clamp on live filters (thr = -inf) and every live
   // (frame, filter) below `cand` dB goes on the warp's candidate list.  Pass 1 (only when a candidate
   // list overflowed) redoes the quads clamped at the now known threshold.
@@ -391,6 +382,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
   // up to 201 samples) plus the ragged end; Parseval with window <= 1 and mel weights <= 1 gives
   // mel <= 400 * E_frame.  Anything 80 dB below the bound or higher can never be clamped by top_db.
   env.csync();                                            // #0: every rank's atom maximum is visible
+  float cand = -3.0e38f;
   {
     double amax = 0.0, eleft = 0.0;
     for (int rr = 0; rr < NR; ++rr) {
@@ -402,9 +394,10 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     if (P.parts & kPartWave) cand = 3.0102999566398120f * env.log2(fmaxf(bound, 1e-30f)) - 80.0f + 0.01f;
     else cand = 3.0e38f;                                  // no atoms: every live value is a candidate (overflow -> clamped pass)
   }
+  float thr = -3.0e38f, gmax = -3.0e38f, gmin = 3.0e38f;
   int ncand = 0;                                           // warp-uniform length of this warp's candidate list
   int ovf_task = 0x7fffffff;                               // warp-uniform: first task (quad) whose candidates did not fit
-  bool slow_w = false;                                     // slow: some warp of this CTA overflowed; slow_w: this warp did
+  bool fix = false, slow = false, slow_w = false;          // slow: some warp of this CTA overflowed; slow_w: this warp did
   for (int pass = 0; pass < 2; ++pass) {
     const float cand_p = (pass == 0) ? cand : -3.0e38f;
       float dmax[S], dmin[S];
@@ -778,7 +771,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       part->slow_pass = slow ? 1 : 0;
     }
   }
-  }                                                       // phases
   env.csync();                                            // #2: all partial moments and atoms are visible
 
   // ---------------------------------------------------------------- rank 0: merge and assemble the row

@@ -32,6 +32,15 @@ namespace msa {
 
 constexpr int kRing = 2048;     // fp16 samples of the padded signal a warp keeps staged (positions modulo kRing)
 
+// Where padded position p lives in the ring (in samples).  The ring is 64 rows of 32 samples (64 bytes); ldmatrix reads
+// one 16-byte chunk from each of 8 CONSECUTIVE rows, which would hit only two of the eight 16-byte bank groups, so the
+// four chunks of row R are stored XOR-swizzled by (R / 2) % 4: eight consecutive rows then cover all eight groups
+// (ldmatrix and the read-back of the input in the residual are conflict-free).
+MSA_FN int ring_off(int p) {
+  const int R = p >> 5, c = (p >> 3) & 3;
+  return ((R & 63) << 5) | ((c ^ ((R >> 1) & 3)) << 3) | (p & 7);
+}
+
 #define MSA_R(expr) [&](int li_) { return (expr); }
 
 // x: the segment; T samples; [q_begin, q_end): this CTA's quads; ring: this warp's kRing fp16 samples (16-byte aligned)
@@ -88,7 +97,8 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
       u32 w[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) w[i] = h2_pack(v[2 * i], v[2 * i + 1]);
-      env.st16(ring + (p & (kRing - 1)), w);
+      env.st8(ring + ring_off(p), w);                                   // two chunks of one row
+      env.st8(ring + ring_off(p + 8), w + 4);
     });
     staged += 512;
   };
@@ -115,7 +125,7 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
           for (int jj = 0; jj < 2; ++jj) {
             env.lanes([&](int lane, int li) {
               const int n1 = (lane & 7) + 8 * ((lane >> 3) & 1), tile = 2 * jj + (lane >> 4);
-              rp[li] = ring + ((kHopP * (fa + fr) + 32 * n1 + 8 * tile) & (kRing - 1));
+              rp[li] = ring + ring_off(kHopP * (fa + fr) + 32 * n1 + 8 * tile);
             });
             if (fr == 0) env.ldsm4t(MSA_R(&bre[li_][2 * jj][0]), MSA_R(rp[li_]));
             else env.ldsm4t(MSA_R(&bim[li_][2 * jj][0]), MSA_R(rp[li_]));
@@ -310,7 +320,7 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int p = kHopP * blk + 32 * (g & 3) + 8 * j + 2 * tq;
-              const u32 xv = env.lds1(reinterpret_cast<const u32*>(ring + (p & (kRing - 1))));
+              const u32 xv = env.lds1(reinterpret_cast<const u32*>(ring + ring_off(p)));
               const u32 r = h2_abs(h2_fnma(done[li][j], k23, xv));
               const float r0 = h2_lo(r), r1 = h2_hi(r);
               s1 += r0 + r1;

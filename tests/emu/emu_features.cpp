@@ -34,7 +34,6 @@ struct CpuCluster {
 struct CpuEnv {
   static constexpr int kStates = 32;
   int tid, nthreads, lane, warp, nwarps, rank, nranks, cluster_id;
-  bool mfcc_first = false;
   std::barrier<>* block;
   CpuCluster* cl;
 
@@ -62,7 +61,7 @@ struct CpuEnv {
   uint32_t ldu(const uint32_t* p) { return *p; }
   float cospi(float v) { return (float)std::cos(3.14159265358979323846 * (double)v); }
   template <class InT> void ld16(const InT* x, int idx, float* v) { for (int i = 0; i < 16; ++i) v[i] = ld(x + idx + i); }
-  void st16(uint16_t* dst, const uint32_t* w) { std::memcpy(dst, w, 32); }
+  void st8(uint16_t* dst, const uint32_t* w) { std::memcpy(dst, w, 16); }
   uint32_t lds1(const uint32_t* p) { return *p; }
   void lds2(uint32_t* d, const uint32_t* p) { d[0] = p[0]; d[1] = p[1]; }
   void lds4(uint32_t* d, const uint32_t* p) { for (int i = 0; i < 4; ++i) d[i] = p[i]; }
@@ -156,7 +155,7 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
   if (T <= kNfftM / 2) parts &= ~kPartMfcc;
   FeatParams P{};
   P.wav = wav; P.is_s16 = is_s16; P.B = B; P.T = T; P.noise_n = (int)(0.05 * (double)T);
-  P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.dbscratch = dbscratch; P.tab = &tab; P.flags = flags; P.parts = parts; P.num_sms = 1;
+  P.emo8 = emo8; P.feat31 = feat31; P.detail = detail; P.dbg_mfcc = dbg_mfcc; P.dbscratch = dbscratch; P.tab = &tab; P.flags = flags; P.parts = parts;
   const FeatLayout lay = feat_layout(T, nranks, nwarps);
   for (int seg = 0; seg < B; ++seg) {
     CpuCluster cl(nranks * nwarps);
@@ -172,7 +171,7 @@ extern "C" int emu_features_ws(const void* wav, int is_s16, int B, int T, int nr
     for (int r = 0; r < nranks; ++r)
       for (int w = 0; w < nwarps; ++w)
         th.emplace_back([&, r, w]() {
-          CpuEnv env{w * 32, nwarps * 32, 0, w, nwarps, r, nranks, seg, (seg & 1) != 0, bars[r].get(), &cl};   // odd segments: MFCC before the round trip
+          CpuEnv env{w * 32, nwarps * 32, 0, w, nwarps, r, nranks, seg, bars[r].get(), &cl};
           if (is_s16) features_cta<CpuEnv, int16_t>(env, P, cl.smem[r]);
           else features_cta<CpuEnv, float>(env, P, cl.smem[r]);
         });
