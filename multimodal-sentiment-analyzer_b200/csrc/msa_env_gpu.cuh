@@ -36,6 +36,8 @@ struct GpuEnv {
   __device__ __forceinline__ float ld_last(const float* p) { return __ldcs(p); }
   __device__ __forceinline__ float ld_last(const int16_t* p) { return s16_to_f32((int)__ldcs(p)); }
 
+  // request the 128-byte line at p into L1 (no register, no wait)
+  __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
   // request the 128-byte line at p into L2 (no register, no wait)
   __device__ __forceinline__ void prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

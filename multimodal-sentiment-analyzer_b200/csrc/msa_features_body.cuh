@@ -483,6 +483,16 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         }
         const int s0 = kHopM * m0 - kNfftM / 2;
         const bool interior = (s0 >= 0) && (s0 + 5 * kHopM <= T);
+        // the next quad of this warp reads samples s0 + 800 .. s0 + 1799 (the first 200 of them are in L1 already):
+        // requested into L1 now, one 128-byte line per lane, so that its first loads do not wait for L2 / HBM
+        if (task + 1 < t_end) {
+          env.lanes([&](int lane, int li) {
+            (void)li;
+            constexpr int kPerLine = 128 / (int)sizeof(InT);
+            const int tn = s0 + 5 * kHopM + lane * kPerLine;
+            if (lane * kPerLine < 4 * kHopM + kPerLine && tn >= 0 && tn < T) env.prefetch_l1(x + tn);
+          });
+        }
         for (int h = 0; h < 2; ++h) {
           env.lanes([&](int lane, int li) {
             (void)li;

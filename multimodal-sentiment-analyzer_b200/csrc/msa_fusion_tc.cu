@@ -246,18 +246,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
     mbar_wait(&tail->accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float sum = 0.0f, sumsq = 0.0f;
+    // Row statistics of this CTA's NC columns as (mean, centred sum of squares), formed from sums SHIFTED by the row's
+    // first value: sum (x - s) and sum (x - s)^2 with s within a few sigma of the mean lose nothing when |mean| >> sigma
+    // (a trained checkpoint's biases), unlike sum x^2 / n - mean^2.  One sweep over tensor memory, like before.
+    float sum = 0.0f, sumsq = 0.0f, shift = 0.0f;
     for (int c = 0; c < NC; c += 32) {
       float v[32];
       tmem_ld32(trow + c, v);
+      if (c == 0) shift = v[0] + tail->bias[0];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float x = v[i] + tail->bias[c + i];
+        const float x = v[i] + tail->bias[c + i] - shift;
         sum += x;
         sumsq = fmaf(x, x, sumsq);
       }
     }
-    tail->stats[row_in_tile] = make_float2(sum, sumsq);
+    const float dm = sum * (1.0f / (float)NC);
+    tail->stats[row_in_tile] = make_float2(shift + dm, fmaxf(sumsq - sum * dm, 0.0f));     // (mean_i, M2_i)
   }
 
   cg::cluster_group cluster = cg::this_cluster();
@@ -266,16 +271,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
   if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue pass 2: normalise, ReLU, store / project
     const int row_in_tile = (warp & 3) * 32 + lane;
-    float2 tot = make_float2(0.0f, 0.0f);
+    // combine the CL partial (mean_i, M2_i) of equal size NC (Chan et al.): mean = avg mean_i, M2 = sum M2_i + NC sum (mean_i - mean)^2;
+    // rank order, so every CTA of the cluster forms the same bits
+    float mi[CL], msum = 0.0f, m2 = 0.0f;
 #pragma unroll
-    for (int r = 0; r < CL; ++r) {                                       // rank order: every CTA adds the same bits
+    for (int r = 0; r < CL; ++r) {
       const float2* peer = (CL > 1) ? cluster.map_shared_rank(&tail->stats[0], r) : &tail->stats[0];
       const float2 o = peer[row_in_tile];
-      tot.x += o.x;
-      tot.y += o.y;
+      mi[r] = o.x;
+      msum += o.x;
+      m2 += o.y;
     }
-    const float mean = tot.x / (float)ep.n_total;
-    const float var = fmaxf(tot.y / (float)ep.n_total - mean * mean, 0.0f);
+    const float mean = msum * (1.0f / (float)CL);
+    float spread = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CL; ++r) spread = fmaf(mi[r] - mean, mi[r] - mean, spread);
+    const float var = (m2 + (float)NC * spread) / (float)ep.n_total;
     const float rstd = rsqrtf(var + 1e-5f);
     const uint32_t trow = tail->tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int row = m0 + row_in_tile;
@@ -383,15 +394,21 @@ struct PrepArgs {
   int B, Bp, nmod;
 };
 
+constexpr int kPrepMaxK = 832;                                           // 783 padded to a multiple of 64
+
 __global__ void __launch_bounds__(256) tc_input_prep_kernel(const PrepArgs a) {
+  // the warp's row is normalised with lane-strided columns (coalesced loads), staged as bf16 pairs in shared memory and
+  // written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at a quarter of the HBM rate
+  __shared__ __align__(16) __nv_bfloat16 stage[8][2][kPrepMaxK];
   const int m = blockIdx.y;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int w = threadIdx.x >> 5;
+  const int row = blockIdx.x * 8 + w, lane = threadIdx.x & 31;
   if (row >= a.Bp) return;
   const int d = a.d[m], kpad = a.kpad[m];
-  __nv_bfloat16* hi = a.hi[m] + (size_t)row * kpad;
-  __nv_bfloat16* lo = a.lo[m] + (size_t)row * kpad;
+  uint4* hi = reinterpret_cast<uint4*>(a.hi[m] + (size_t)row * kpad);
+  uint4* lo = reinterpret_cast<uint4*>(a.lo[m] + (size_t)row * kpad);
   if (row >= a.B) {
-    for (int c = lane; c < kpad; c += 32) { hi[c] = __float2bfloat16_rn(0.0f); lo[c] = __float2bfloat16_rn(0.0f); }
+    for (int c = lane; c < kpad / 8; c += 32) { hi[c] = make_uint4(0u, 0u, 0u, 0u); lo[c] = make_uint4(0u, 0u, 0u, 0u); }
     return;
   }
   const float* x = a.x[m] + (size_t)row * d;
@@ -423,10 +440,14 @@ __global__ void __launch_bounds__(256) tc_input_prep_kernel(const PrepArgs a) {
       float y = 0.0f;
       if (c < d) y = (v[i < 25 ? i : 24] - mean) * rstd * a.gamma[m][c] + a.beta[m][c];
       const __nv_bfloat16 h = __float2bfloat16_rn(y);
-      hi[c] = h;
-      lo[c] = __float2bfloat16_rn(y - __bfloat162float(h));
+      stage[w][0][c] = h;
+      stage[w][1][c] = __float2bfloat16_rn(y - __bfloat162float(h));
     }
   }
+  __syncwarp();
+  const uint4* sh = reinterpret_cast<const uint4*>(stage[w][0]);
+  const uint4* sl = reinterpret_cast<const uint4*>(stage[w][1]);
+  for (int c = lane; c < kpad / 8; c += 32) { hi[c] = sh[c]; lo[c] = sl[c]; }
 }
 
 // ------------------------------------------------------------------------------ host side

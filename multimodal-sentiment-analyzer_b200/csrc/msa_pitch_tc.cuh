@@ -99,6 +99,11 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
       for (int i = 0; i < 8; ++i) w[i] = h2_pack(v[2 * i], v[2 * i + 1]);
       env.st8(ring + ring_off(p), w);                                   // two chunks of one row
       env.st8(ring + ring_off(p + 8), w + 4);
+      // the chunk after this one is requested into L1 now (one 128-byte line per lane), so that its loads, one quad
+      // from now, do not wait for L2 / HBM
+      constexpr int kPerLine = 128 / (int)sizeof(InT);
+      const int tn = staged + 512 - kNfftP / 2 + lane * kPerLine;
+      if (lane * kPerLine < 512 && tn >= 0 && tn < T) env.prefetch_l1(x + tn);
     });
     staged += 512;
   };

@@ -50,6 +50,7 @@ struct CpuEnv {
   float ld(const float* p) { return *p; }
   float ld(const int16_t* p) { return (float)*p * (1.0f / 32768.0f); }
   void prefetch(const void*) {}
+  void prefetch_l1(const void*) {}
   float ld_last(const float* p) { return ld(p); }
   float ld_last(const int16_t* p) { return ld(p); }
   template <class InT> void ld4(const InT* x, int idx, int T, float* v) {

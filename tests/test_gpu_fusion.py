@@ -300,3 +300,28 @@ def test_streaming_window_equals_offline(use_graph, with_text):
         assert torch.equal(o["audio_row"], row[0]) and torch.equal(o["fused_emotion"], logits[0]) and o["argmax"] == int(amax[0].item())
         if o["host"] is not None:
             assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == o["argmax"]
+
+
+@pytest.mark.parametrize("n", [300, 5000], ids=["128-column tiles", "512-column tiles"])
+def test_layernorm_rows_with_mean_far_from_zero(n):
+    """A trained checkpoint can have |row mean| >> row sigma in front of a LayerNorm (large Linear biases): the fused
+    epilogue's statistics (shifted sums + Chan combine across the cluster) must not lose the variance there.  Biases
+    4.0 + 0.05 N(0,1) in front of every LayerNorm; both tensor-core tile shapes; logits abs 1e-3 vs the fp64 oracle."""
+    dev = need_gpu()
+    import msa_b200
+    from msa_b200 import _lib
+    assert _lib.lib().msa_fusion_set_impl(0) == 0
+    sd = synth.fusion_state(777, trained_like=True)
+    rng = np.random.default_rng(5)
+    for name in ("face_proj", "audio_proj", "text_proj", "face_processor.3", "audio_processor.3", "text_processor.3", "fusion.0", "fusion.4", "fusion2"):
+        sd[name + ".bias"] = (4.0 + 0.05 * rng.standard_normal(sd[name + ".bias"].shape)).astype(np.float32)
+    m = msa_b200.AdvancedFusionModel(device="cuda:0")
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=True)
+    (f, a, t), (fd, ad, td) = _inputs(n, dev)
+    for text_np, text_d, fuse in ((t, td, fu.fuse_all), (None, None, None)):
+        logits, amax = m.fused_with_argmax(fd, ad, text_d)
+        torch.cuda.synchronize()
+        ref = fu.fuse_all(sd, f, a, t) if text_np is not None else fu.fuse_face_audio(sd, f, a)
+        d = np.abs(logits.cpu().numpy() - ref)
+        assert d.max() < 1e-3, (n, text_np is not None, float(d.max()))
+        assert (amax.cpu().numpy() == ref.argmax(1)).mean() >= 0.999
