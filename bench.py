@@ -202,6 +202,21 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` BEFORE the pinned host buffers are allocated
+    (first touch puts them on that NUMA node): with 4-8 ranks uploading at once, buffers that sit on the other socket
+    cross the inter-socket link and cap the box's aggregate host-to-device rate.  Returns a short description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return {"cpus_before": before, "cpus_after": len(os.sched_getaffinity(0)), "how": "nvmlDeviceSetCpuAffinity"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:80]}
+
+
 def run_native(args):
     # NCCL prints its "NCCL version ..." banner (any NCCL_DEBUG level from VERSION up) on stdout when the first
     # communicator is created; stdout must carry ONE JSON line.  Send NCCL's log to stderr, and, because a pod may
@@ -217,6 +232,7 @@ def run_native(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_numa(local)
     if world > 1:
         sys.stdout.flush()
         saved_stdout = os.dup(1)
@@ -238,7 +254,7 @@ def run_native(args):
 
     import msa_b200
     from msa_b200 import _lib
-    from msa_b200.pipeline import ROW_WORDS, gather_rows, pack_rows
+    from msa_b200.pipeline import ROW_WORDS, gather_rows_async, pack_rows
     from msa_b200 import synth
 
     S = args.segments
@@ -257,6 +273,7 @@ def run_native(args):
     lib = _lib.lib()
 
     launches = {"n": 0}
+    pending = {"g": None}
 
     def step_resident():
         row = ana.analyze_batch(wav_dev)
@@ -265,7 +282,11 @@ def run_native(args):
         launches["n"] += lib.msa_last_launch_count()
         rows = pack_rows(row, logits, amax, rank * S)
         launches["n"] += lib.msa_last_launch_count()
-        return gather_rows(rows, S * world, world, rank)
+        # the one collective of the path runs behind this step's kernels on NCCL's stream and overlaps the next step; the
+        # gather of the step before is waited for here (stream-level), so every step's table is complete inside the timed region
+        pend = gather_rows_async(rows, S * world, world, rank)
+        prev, pending["g"] = pending["g"], pend
+        return prev.wait() if prev is not None else None
 
     pipe = msa_b200.SegmentPipeline(ana, model)
 
@@ -273,9 +294,11 @@ def run_native(args):
         # public host-buffer API: chunked upload on a copy stream overlapped with the kernels, one D2H of the rows
         return pipe.run_host(pcm_host, face_host, text_host, rows_host, first_id=rank * S, chunk=args.chunk)
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, tail=None):
         for _ in range(warmup):
             fn()
+        if tail is not None:
+            tail()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -284,6 +307,8 @@ def run_native(args):
         e0.record()
         for _ in range(steps):
             fn()
+        if tail is not None:
+            tail()                                                     # the last step's gather is inside the timed region
         e1.record()
         torch.cuda.synchronize()
         if world > 1:
@@ -298,7 +323,12 @@ def run_native(args):
         sampler.start()
         time.sleep(0.3)
     launches["n"] = 0
-    ms_total = timed(step_resident, args.steps, args.warmup)
+
+    def resident_loop_tail():
+        if pending["g"] is not None:
+            pending["g"].wait()
+            pending["g"] = None
+    ms_total = timed(step_resident, args.steps, args.warmup, tail=resident_loop_tail)
     launches_timed = launches["n"] * args.steps // max(1, args.steps + args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
@@ -450,6 +480,7 @@ def run_native(args):
             "fusion_only_65536": fus65,
             "stream_latency": stream,
             "reference_api_call": api,
+            "host_affinity": affinity,
             "gpu_launches": int(launches_timed),
             "clocks": clocks,
         }

@@ -64,6 +64,42 @@ def gather_rows(local_rows: torch.Tensor, n_total: int, world_size: int, rank: i
     return torch.cat([out[r * cap: r * cap + sizes[r]] for r in range(world_size)], dim=0)
 
 
+class PendingGather:
+    """Result of ``gather_rows_async``: the all_gather runs on NCCL's own stream behind the kernels that produced the
+    local rows, and the compute stream goes on with the next batch.  ``wait()`` makes the current stream wait for it and
+    returns the gathered [n_total, 40] table."""
+
+    def __init__(self, out, work, sizes, cap, keep):
+        self._out, self._work, self._sizes, self._cap, self._keep = out, work, sizes, cap, keep
+
+    def wait(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()                    # stream-level wait (the host does not block)
+            self._work = None
+        if self._sizes is None or all(n == self._cap for n in self._sizes):
+            return self._out                     # equal shards: the gathered buffer IS the table (no copy)
+        return torch.cat([self._out[r * self._cap: r * self._cap + n] for r, n in enumerate(self._sizes)], dim=0)
+
+
+def gather_rows_async(local_rows: torch.Tensor, n_total: int, world_size: int, rank: int, group=None) -> PendingGather:
+    """``gather_rows`` without stalling the compute stream: the collective is latency-bound (160 bytes per segment), so a
+    step that waits for it pays ~45 us for nothing; issued asynchronously it overlaps the next batch's kernels
+    (offline_processor.py only needs the table when all segments are done, :259)."""
+    if world_size == 1:
+        return PendingGather(local_rows, None, None, 0, None)
+    import torch.distributed as dist
+    sizes = [shard_range(n_total, world_size, r)[1] - shard_range(n_total, world_size, r)[0] for r in range(world_size)]
+    cap = max(sizes)
+    if local_rows.shape[0] == cap:
+        buf = local_rows
+    else:
+        buf = torch.zeros(cap, ROW_WORDS, device=local_rows.device, dtype=torch.float32)
+        buf[: local_rows.shape[0]] = local_rows
+    out = torch.empty(world_size * cap, ROW_WORDS, device=local_rows.device, dtype=torch.float32)
+    work = dist.all_gather_into_tensor(out, buf, group=group, async_op=True)
+    return PendingGather(out, work, sizes, cap, (buf, local_rows))
+
+
 def aggregate_speakers(argmax: torch.Tensor, speaker: torch.Tensor, n_speakers: int) -> Dict[str, torch.Tensor]:
     """offline_processor.py:259-298 on device: per-speaker label histogram, dominant emotion (mode)
     and the starts of three-in-a-row "patterns" within each speaker's own segment sequence."""
@@ -171,8 +207,11 @@ class SegmentPipeline:
 
     @torch.no_grad()
     def run_sharded(self, waves_local, face_local, text_local, n_total: int, world_size: int, rank: int,
-                    emotion_probs=None, group=None) -> torch.Tensor:
-        """This rank's shard through the pipeline, then the single result gather."""
+                    emotion_probs=None, group=None, async_gather: bool = False):
+        """This rank's shard through the pipeline, then the single result gather.  ``async_gather=True`` returns a
+        ``PendingGather`` (the collective overlaps whatever the caller launches next; ``.wait()`` gives the table)."""
         begin, _ = shard_range(n_total, world_size, rank)
         rows = self.run(waves_local, face_local, text_local, emotion_probs, first_id=begin)
+        if async_gather:
+            return gather_rows_async(rows, n_total, world_size, rank, group)
         return gather_rows(rows, n_total, world_size, rank, group)

@@ -111,7 +111,7 @@ def _gather_worker(rank, world, port, n_total, out_dir):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import msa_b200  # noqa: F401
-    from msa_b200.pipeline import ROW_WORDS, gather_rows, shard_range, unpack_rows
+    from msa_b200.pipeline import ROW_WORDS, gather_rows, gather_rows_async, shard_range, unpack_rows
     b, e = shard_range(n_total, world, rank)
     g = torch.Generator().manual_seed(1000)                      # every rank draws the same full table ...
     full_audio, full_logits = torch.randn(n_total, 31, generator=g), torch.randn(n_total, 7, generator=g)
@@ -122,6 +122,8 @@ def _gather_worker(rank, world, port, n_total, out_dir):
     assert torch.equal(u["audio_row"], full_audio) and torch.equal(u["logits"], full_logits)
     assert u["segment_id"].tolist() == list(range(n_total))
     assert torch.equal(u["argmax"].long(), full_logits.argmax(1))
+    pend = gather_rows_async(rows, n_total, world, rank)                      # the overlapped form gives the same table
+    assert torch.equal(pend.wait().view(torch.int32), table.view(torch.int32))
     np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([table.shape[0]]))
     dist.barrier()
     dist.destroy_process_group()
