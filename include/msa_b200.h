@@ -33,15 +33,13 @@ extern "C" {
 
 /* flags of msa_features_* */
 #define MSA_FEAT_STRICT_NAN 1 /* mono intensity = NaN exactly like audio_analyzer.py:194-196 (default) */
-#define MSA_FEAT_NO_LOCKSTEP 2 /* tuning: no per-quad block barrier in the STFT-512 phase (also MSA_FEAT_LOCKSTEP=0) */
-#define MSA_FEAT_FOLD_WAVE 4 /* opt-in (also MSA_FEAT_FOLD=1 in the environment): the wave statistics (rhythm, speech_rate,
-                              * snr, consistency) are formed by the STFT-512 quads from the samples they hold anyway, instead of
-                              * a pass of their own over the segment: one read of the waveform fewer, bit-identical results.
-                              * Applies when parts has both MSA_PART_WAVE and MSA_PART_PITCH; detail[79] = 1 for rows it produced. */
+                              /* bits 2 and 4 were tuning / experiment switches of round 1 (lockstep barrier, folded wave statistics):
+                               * removed with the fp32 STFT-512 path they belonged to; set bits are ignored */
 /* parts mask: which feature groups to compute (the rest take the reference's exception defaults) */
 #define MSA_PART_WAVE 1  /* rhythm, speech_rate, snr, consistency */
 #define MSA_PART_MFCC 2  /* timbre, clarity */
-#define MSA_PART_PITCH 4 /* STFT-512 -> ISTFT residual */
+#define MSA_PART_PITCH 4 /* STFT-512 -> ISTFT residual (fp16 round trip on the tensor cores: the feature is the mean of the
+                          * z-scored residual, |v| <= 1e-6 whatever the residual's precision; detail[65:68] = its mean, std, max) */
 #define MSA_PART_ALL 7
 
 #define MSA_DETAIL_STRIDE 96
@@ -71,7 +69,7 @@ int msa_features_smem_bytes(int T, int cluster_size);
  *           (emotion8, pitch, intensity, timbre13, speech_rate, rhythm3), [27:31] the four quality
  *           floats, [32:63] the full LayerNorm(31) row (NaN where the reference is NaN),
  *           [64:80] diagnostics (top_db max, residual mean/std/max, energies, counts, clamped-pass flag, min dB,
- *           candidate level, clamp flag, [79] = 1 if MSA_FEAT_FOLD_WAVE produced the row)
+ *           candidate level, clamp flag)
  *   dbg_mfcc [B, T/200+1, 13] out or NULL: the MFCC matrix (frames x coefficients)
  *   cluster_size 0 = auto, else 1/2/4/8
  */
@@ -173,6 +171,15 @@ int msa_pitch_outputs(int T);
 int msa_voiced_frames(int T);
 int msa_pitch_track_f32(const float* wav, int B, int T, int32_t* lags, float* f0, int32_t* voiced, void* stream);
 int msa_pitch_track_s16(const int16_t* pcm, int B, int T, int32_t* lags, float* f0, int32_t* voiced, void* stream);
+/* Spectral timbre descriptors and the onset envelope per frame of the MFCC's own STFT grid (n_fft 400, hop 200, periodic
+ * Hann, centre + reflect: the transform inside torchaudio.transforms.MFCC, audio_analyzer.py:207-210):
+ *   out4 [B, msa_spectral_frames(T), 4] fp32 = spectral centroid [Hz] (= torchaudio.functional.spectral_centroid; NaN for
+ *   a silent frame like torchaudio), roll-off [Hz] (first bin whose cumulative magnitude reaches 85 %), spectral flux
+ *   (L2 norm of the magnitude difference to the previous frame) and onset strength (mean over the 128 HTK mel bands of
+ *   the positive log-power difference).  T must exceed 200 (torch.stft's reflect padding).  Oracle: oracle/descriptors_np.py. */
+int msa_spectral_frames(int T);
+int msa_spectral_f32(const float* wav, int B, int T, float* out4, void* stream);
+int msa_spectral_s16(const int16_t* pcm, int B, int T, float* out4, void* stream);
 /* probs [B,7] = softmax(logits [B,7]) (fusion_model.py:94 returns raw logits; consumers argmax them). */
 int msa_softmax7(const float* logits, int B, float* probs, void* stream);
 

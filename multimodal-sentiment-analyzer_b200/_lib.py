@@ -43,6 +43,9 @@ _SIGNATURES = {
     "msa_voiced_frames": (c_int, [c_int]),
     "msa_pitch_track_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "msa_pitch_track_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "msa_spectral_frames": (c_int, [c_int]),
+    "msa_spectral_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "msa_spectral_s16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "msa_softmax7": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "msa_pack_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "msa_nan_to_num": (c_int, [c_void_p, ctypes.c_longlong, c_void_p]),

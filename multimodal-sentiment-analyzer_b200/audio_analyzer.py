@@ -148,6 +148,22 @@ class AudioAnalyzer:
                        "msa_pitch_track")
         return {"f0": f0, "lags": lags, "voiced": voiced}
 
+    def spectral_descriptors(self, waveforms: torch.Tensor) -> dict:
+        """Additive output (NOT computed by the reference): per frame of the MFCC's STFT grid
+        (n_fft 400, hop 200) the spectral centroid [Hz] (= torchaudio.functional.spectral_centroid), the 85 % roll-off
+        [Hz], the spectral flux and an onset-strength envelope.  waveforms [B, T] fp32 / int16 on the device ->
+        {"centroid", "rolloff", "flux", "onset"}: [B, T // 200 + 1] fp32 each."""
+        w = waveforms.to(self.device)
+        if w.dtype != torch.int16:
+            w = w.float()
+        w = w.contiguous()
+        B, T = w.shape
+        out = torch.empty(B, self._lib.msa_spectral_frames(T), 4, device=self.device, dtype=torch.float32)
+        fn = self._lib.msa_spectral_s16 if w.dtype == torch.int16 else self._lib.msa_spectral_f32
+        with _lib.on_device(self.device):
+            _lib.check(fn(_lib.ptr(w), B, T, _lib.ptr(out), _lib.current_stream_ptr(self.device)), "msa_spectral")
+        return {"centroid": out[..., 0], "rolloff": out[..., 1], "flux": out[..., 2], "onset": out[..., 3]}
+
     # ------------------------------------------------------------------ reference API
     def analyze(self, audio_path: str, speaker_id: str) -> AudioAnalysis:
         """audio_analyzer.py:56-150: load, resample to 16 kHz, all features, LayerNorm(31), slices."""

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libmsa_b200.so")
-SOURCES = ["msa_api.cu", "msa_features.cu", "msa_fusion.cu", "msa_fusion_tc.cu", "msa_fusion_rows.cu", "msa_aggregate.cu", "msa_ingest.cu", "msa_descriptors.cu"]
+SOURCES = ["msa_api.cu", "msa_features.cu", "msa_fusion.cu", "msa_fusion_tc.cu", "msa_fusion_rows.cu", "msa_aggregate.cu", "msa_ingest.cu", "msa_descriptors.cu", "msa_spectral.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

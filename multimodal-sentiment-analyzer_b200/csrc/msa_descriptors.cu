@@ -10,10 +10,11 @@
 //           segment-level `energy > 0.1 * energy.mean()` (/root/reference/src/analyzers/audio_analyzer.py:223-228).
 //   probs   softmax over the 7 fused logits (fusion_model.py:94 leaves them raw).
 //
-// One warp per 10 ms frame (CTAs of 64 frames): the frame and its look-ahead sit in a shared-memory row; lane l
-// owns 7 consecutive lags, so the shifted samples slide through a register window and a step costs two
-// shared-memory loads for 7 FMAs; the energies of the shifted frames come from one fp64 prefix sum per frame.
-// Time-domain on purpose: the direct sums keep the arg-max decisions within rounding distance of torch's.
+// One warp per 10 ms frame (CTAs of 64 frames): the frame and its look-ahead sit in a shared-memory row; lane l takes
+// lags l + 1, l + 33, ...  Every sum of 160 terms (<s1, s2>, |s1|^2, |s2|^2) is formed in fp32 in EXACTLY the order of
+// the oracle's (and numpy's) pairwise summation - products rounded before they are added, two blocks of 80, eight
+// running sums per block combined as ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7)) - so that the NCCF values, and
+// with them every arg-max decision including the near-ties, are bit-identical to oracle/descriptors_np.py.
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -24,14 +25,31 @@
 namespace msa {
 
 constexpr int kPFrame = 160, kPLags = 189, kPLagMin = 5, kPMedWin = 30, kPWarps = 8;
-constexpr int kPLpl = 7;                       // lags per lane
 constexpr int kPChunk = 64;                    // frames per CTA of the lag kernel (8 per warp)
-constexpr int kPRow = 416;                     // frame + look-ahead of the last lane's window, rounded to 32
+constexpr int kPRow = 352;                     // frame + 189 samples of look-ahead, rounded to 32
 constexpr int kVWin = 400, kVHop = 160;
 
 __device__ __forceinline__ float pt_load(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float pt_load(const int16_t* p) {
   return __fmaf_rn(__int_as_float(0x4B400000 + (int)__ldg(p)), 1.0f / 32768.0f, -384.0f);
+}
+
+// sum_i a[i] * b[i] over 160 terms in numpy's pairwise order (see the header): no fused multiply-adds
+__device__ __forceinline__ float np_dot160(const float* __restrict__ a, const float* __restrict__ b) {
+  float total = 0.0f;
+#pragma unroll 1
+  for (int blk = 0; blk < 2; ++blk) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __fmul_rn(a[80 * blk + j], b[80 * blk + j]);
+#pragma unroll 3
+    for (int i = 8; i < 80; i += 8)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], __fmul_rn(a[80 * blk + i + j], b[80 * blk + i + j]));
+    const float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])), __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    total = (blk == 0) ? res : __fadd_rn(total, res);
+  }
+  return total;
 }
 
 // grid (frame chunks, B): a CTA takes kPChunk consecutive frames of one segment (fine-grained CTAs keep the last
@@ -40,9 +58,7 @@ template <class InT>
 __global__ void __launch_bounds__(kPWarps * 32) pitch_lags_kernel(const InT* __restrict__ wav, int T, int nf,
                                                                   int32_t* __restrict__ lags_out) {
   __shared__ float rows[kPWarps][kPRow];
-  __shared__ double psum[kPWarps][kPRow + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* P = psum[warp];
   const InT* x = wav + (size_t)blockIdx.y * T;
   int32_t* lags = lags_out + (size_t)blockIdx.y * nf;
   float* s = rows[warp];
@@ -56,66 +72,20 @@ __global__ void __launch_bounds__(kPWarps * 32) pitch_lags_kernel(const InT* __r
       s[lane + 32 * k] = (t < T) ? pt_load(x + t) : 0.0f;          // torch pads the waveform with zeros
     }
     __syncwarp();
-    // energies of the frame and of every shifted frame from ONE fp64 prefix sum of the squares (lane l scans the
-    // 13 consecutive samples 13 l .. 13 l + 12, a shuffle scan adds the lane offsets): e2[lag] = P[lag + 160] - P[lag]
-    // is exact to fp64, which halves the FMAs of the correlation loop below
-    {
-      double run[kPRow / 32];
-      double tot = 0.0;
-#pragma unroll
-      for (int k = 0; k < kPRow / 32; ++k) { const double v = (double)s[(kPRow / 32) * lane + k]; tot = fma(v, v, tot); run[k] = tot; }
-      double off = tot;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += t; }
-      off -= tot;                                                  // exclusive offset of this lane
-#pragma unroll
-      for (int k = 0; k < kPRow / 32; ++k) P[(kPRow / 32) * lane + k + 1] = off + run[k];
-      if (lane == 0) P[0] = 0.0;
-    }
-    __syncwarp();
-    const float e1 = (float)(P[kPFrame] - P[0]);
-    // lane l owns the 7 consecutive lags 1 + 7 l .. 7 + 7 l (27 lanes cover 189 lags).  With consecutive lags the
-    // shifted samples slide through a 7-register window: a step costs one broadcast load of s[i], ONE new
-    // conflict-free load (stride 7 across lanes) and 7 FMAs, instead of one load per multiply-add.
-    float c[kPLpl], e2[kPLpl], b[kPLpl];
-    const float* sl = s + 1 + kPLpl * lane;                        // sl[i + q] = s[i + lag_q]
-#pragma unroll
-    for (int q = 0; q < kPLpl; ++q) {
-      c[q] = 0.0f;
-      b[q] = sl[q];
-      e2[q] = (float)(P[1 + kPLpl * lane + q + kPFrame] - P[1 + kPLpl * lane + q]);
-    }
-    auto steps = [&](int i0, auto nsteps) {
-      constexpr int NS = decltype(nsteps)::value;
-#pragma unroll
-      for (int u = 0; u < NS; ++u) {
-        const float a = s[i0 + u];
-        const float nb = sl[i0 + u + kPLpl];                       // the sample the window gains at the next step
-#pragma unroll
-        for (int q = 0; q < kPLpl; ++q) {
-          const float bv = b[(u + q) % kPLpl];                     // slot of lag q at step u of a block (static index)
-          c[q] = fmaf(a, bv, c[q]);
-        }
-        b[u % kPLpl] = nb;                                         // the slot lag 0 leaves becomes lag 6 of the next step
-      }
-    };
-#pragma unroll 1
-    for (int i0 = 0; i0 + kPLpl <= kPFrame; i0 += kPLpl) steps(i0, std::integral_constant<int, kPLpl>{});
-    steps((kPFrame / kPLpl) * kPLpl, std::integral_constant<int, kPFrame % kPLpl>{});
-    __syncwarp();                                                  // the row is free for the next frame
-    const float n1 = (1e-9f + sqrtf(e1)) * (1e-9f + sqrtf(e1));
+    const float r1 = __fadd_rn(1e-9f, __fsqrt_rn(np_dot160(s, s)));
+    const float n1 = __fmul_rn(r1, r1);                            // (EPS + |s1|) ** 2
     float bv = -3.4e38f, hv = -3.4e38f;
     int bl = 0x7fffffff, hl = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < kPLpl; ++q) {
-      const int lag = 1 + kPLpl * lane + q;
-      const float n2 = (1e-9f + sqrtf(e2[q])) * (1e-9f + sqrtf(e2[q]));
-      const float v = c[q] / n1 / n2;
-      if (lag > kPLagMin && lag <= kPLags) {
-        if (v > bv) { bv = v; bl = lag; }                          // first maximum wins (ascending lags per lane)
+#pragma unroll 1
+    for (int lag = 1 + lane; lag <= kPLags; lag += 32) {           // ascending lags per lane: the first maximum wins
+      const float r2 = __fadd_rn(1e-9f, __fsqrt_rn(np_dot160(s + lag, s + lag)));
+      const float v = __fdiv_rn(__fdiv_rn(np_dot160(s, s + lag), n1), __fmul_rn(r2, r2));
+      if (lag > kPLagMin) {
+        if (v > bv) { bv = v; bl = lag; }
         if (lag <= kPLags / 2 && v > hv) { hv = v; hl = lag; }     // nccf[..., lag_min : lags // 2]
       }
     }
+    __syncwarp();                                                  // the row is free for the next frame
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -125,7 +95,7 @@ __global__ void __launch_bounds__(kPWarps * 32) pitch_lags_kernel(const InT* __r
       const int pl = __shfl_xor_sync(0xffffffffu, hl, o);
       if (pv > hv || (pv == hv && pl < hl)) { hv = pv; hl = pl; }
     }
-    if (lane == 0) lags[f] = (hv > 0.99f * bv) ? hl : bl;          // _combine_max(half, best, thresh = 0.99)
+    if (lane == 0) lags[f] = (hv > __fmul_rn(0.99f, bv)) ? hl : bl;   // _combine_max(half, best, thresh = 0.99)
   }
 }
 

@@ -10,6 +10,12 @@ third-party dependency the reference uses (torchaudio, pinned 2.5.1 in requireme
   voiced_frames                  the per-frame analogue of _analyze_speech_rate's ``energy > 0.1 * energy.mean()``
                                  (audio_analyzer.py:223-228) on the 400/160 rhythm frames of :239-249
   class_probs                    softmax over the 7 fused logits (fusion_model.py:94 leaves them as logits)
+  spectral_descriptors           per frame of the MFCC's STFT grid (n_fft 400, hop 200, periodic Hann, centre + reflect):
+                                 centroid = torchaudio.functional.spectral_centroid (pinned against it), roll-off = first
+                                 bin whose cumulative MAGNITUDE reaches 85 % (librosa.feature.spectral_rolloff's rule),
+                                 flux = L2 norm of the magnitude difference to the previous frame, onset = mean over the
+                                 128 HTK mel bands of the positive part of the log-power difference (the core of
+                                 librosa.onset.onset_strength); stated definitions, first frame 0 for the two differences
 
 tests/golden/descriptors_golden.npz holds torchaudio's own outputs (oracle/make_golden_ingest.py).
 """
@@ -87,3 +93,30 @@ def class_probs(logits: np.ndarray) -> np.ndarray:
     z = z - z.max(-1, keepdims=True)
     p = np.exp(z)
     return p / p.sum(-1, keepdims=True)
+
+
+def stft400_magnitude(x: np.ndarray) -> np.ndarray:
+    """[T] -> [n_frames, 201] fp64 magnitude of the STFT inside torchaudio.transforms.MFCC (n_fft 400, hop 200, periodic
+    Hann, center=True, reflect padding)."""
+    x = np.asarray(x, dtype=np.float64)
+    n = 400
+    xp = np.pad(x, (n // 2, n // 2), mode="reflect")
+    nf = x.shape[0] // 200 + 1
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * np.arange(n) / n)
+    fr = np.lib.stride_tricks.sliding_window_view(xp, n)[::200][:nf]
+    return np.abs(np.fft.rfft(fr * w, axis=-1))
+
+
+def spectral_descriptors(x: np.ndarray) -> np.ndarray:
+    """[T] -> [n_frames, 4] fp64: centroid [Hz], roll-off [Hz], flux, onset strength (definitions in the module header)."""
+    from oracle import features_np as fx
+    S = stft400_magnitude(x)
+    f = 40.0 * np.arange(201)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        cen = (S * f).sum(-1) / S.sum(-1)
+    cum = np.cumsum(S, axis=-1)
+    roll = 40.0 * (cum >= 0.85 * cum[:, -1:]).argmax(-1)
+    flux = np.concatenate([[0.0], np.sqrt(((S[1:] - S[:-1]) ** 2).sum(-1))])
+    L = 10.0 * np.log10(np.maximum((S * S) @ fx.mel_fbanks(), 1e-10))
+    onset = np.concatenate([[0.0], np.maximum(L[1:] - L[:-1], 0.0).mean(-1)])
+    return np.stack([cen, roll, flux, onset], axis=-1)
