@@ -140,6 +140,16 @@ struct GpuEnv {
                  : "=r"(d[0]), "=r"(d[1])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(c0), "r"(c1));
   }
+  // D (16 x 8, fp32) += A (16 x 16, fp16) B (16 x 8, fp16)
+  template <class D, class A, class B> __device__ __forceinline__ void mma_f32(D dg, A ag, B bg) {
+    float* d = dg(0);
+    const u32* a = ag(0);
+    const u32* b = bg(0);
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+  }
+  __device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
   // four transposed 8 x 8 fp16 tiles: lane l supplies the address of row l % 8 of tile l / 8 (8 contiguous values)
   template <class R, class P> __device__ __forceinline__ void ldsm4t(R rg, P pg) {
     u32* r = rg(0);

@@ -59,7 +59,9 @@ constexpr int kK1Groups = 2;                     // load groups in flight per wa
 constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
 constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (the largest MFCC use of a warp's buffer)
 // top_db candidates of one warp live behind the transpose tile: 198 entries of (frame << 7 | filter, dB)
-constexpr int kClampCap = 176;
+constexpr int kClampCap = 166;
+constexpr int kDbRow = 136;                      // row stride (32-bit words) of the quad's [frame][filter] dB table: 128 + 8 keeps the
+                                                 // four rows on different banks for the 8-byte fragment loads
 // a warp's private buffer: MFCC FFT tiles (2 x 3200 B), power rows, the transpose tile + candidate list; the wave-statistics
 // scratch and the fp16 ring of the STFT-512 round trip (4096 B) reuse it in their own phases.  Sized so that the whole
 // layout of a 5 s segment stays below half an SM's shared memory (two CTAs per SM).
@@ -100,6 +102,15 @@ struct FeatLayout {
 };
 
 MSA_FN int ceil_div(int a, int b) { return (a + b - 1) / b; }
+MSA_FN int float_as_int(float f) {
+#ifdef __CUDACC__
+  return __float_as_int(f);
+#else
+  int v;
+  std::memcpy(&v, &f, 4);
+  return v;
+#endif
+}
 MSA_FN float int_as_float(int v) {
 #ifdef __CUDACC__
   return __int_as_float(v);
@@ -158,21 +169,13 @@ MSA_FN double py_clip01(double v) {
 }
 
 // ---- FFT passes (see msa_fft.cuh) ------------------------------------------------------------
-// pass A forward: 16 packed samples -> radix-16 -> twiddle W_N^(n2 k1) -> tile[k1][n2]
+// pass A forward: 16 packed samples -> radix-16 -> twiddle W_N^(n2 k1) -> tile[k1][n2]  (tw: [k1 - 1][n2], row stride ROW)
 template <int ROW> MSA_FN void pass_a_fwd(c32* z, const c32* tw, int n2, c32* tile) {
   dft16<false>(z);
   tile[n2] = z[0];
 #pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) tile[k1 * ROW + n2] = cmul(z[k1], tw[(k1 - 1) * 32 + n2]);
+  for (int k1 = 1; k1 < 16; ++k1) tile[k1 * ROW + n2] = cmul(z[k1], tw[(k1 - 1) * ROW + n2]);
 }
-// pass A inverse: tile[k1][n2] x conj twiddle -> inverse radix-16 -> 16 samples (unnormalised)
-template <int ROW> MSA_FN void pass_a_inv(c32* z, const c32* tw, int n2, const c32* tile) {
-  z[0] = tile[n2];
-#pragma unroll
-  for (int k1 = 1; k1 < 16; ++k1) z[k1] = cmulc(tile[k1 * ROW + n2], tw[(k1 - 1) * 32 + n2]);
-  dft16<true>(z);
-}
-
 enum : int { kOpSum = 0, kOpMax = 1, kOpMin = 2 };
 MSA_FN double red_comb(int op, double a, double b) {
   return op == kOpSum ? a + b : (op == kOpMax ? (a > b ? a : b) : (a < b ? a : b));
@@ -407,7 +410,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
       float* fbuf = reinterpret_cast<float*>(wbuf);
       float cdelta[S][4][4];                                       // [frame][slot] clamp deltas of the current quad
       float dbs[S][4][4];                                          // [frame][slot] mel dB values of the current quad
-      float asum[S][2], casum[S][2];
+      float casum[S][2];
       // DCT of the clamp deltas in cdelta, summed over the lanes in lane order -> casum (v = lane + 32 half): the one
       // arithmetic every way of applying the clamp uses (patch list, saved dB values, recomputed quad)
       auto delta_dct = [&]() {
@@ -415,11 +418,11 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           const float (&cl)[4][4] = cdelta[li];
   #pragma unroll
           for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
-          const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
+          const float* dq = P.tab->dctq;                           // global memory: this path is rare
           static_for<0, kDctQuads>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            const float4 q = dq[i * 32 + lane];
-            const float qc[4] = {q.x, q.y, q.z, q.w};
+            const float qc[4] = {env.ldf(dq + (i * 32 + lane) * 4), env.ldf(dq + (i * 32 + lane) * 4 + 1),
+                                 env.ldf(dq + (i * 32 + lane) * 4 + 2), env.ldf(dq + (i * 32 + lane) * 4 + 3)};
             static_for<0, 4>([&](auto cc) {
               constexpr int c = decltype(cc)::value;
               constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
@@ -609,20 +612,21 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               db[j][s] = d;
             }
           });
+        });
+        // the DCT runs on the tensor cores (below): every dB value goes to shared memory as an fp16 pair (hi, lo) with
+        // hi + lo = d to ~2^-22, word [frame][filter] (rows padded to 136 words: conflict-free fragment loads).  The
+        // power rows this warp just read are dead; a warp barrier separates the last read from the first write.
+        env.wsync();
+        env.lanes([&](int lane, int li) {
+          u32* dbw = reinterpret_cast<u32*>(fbuf);
   #pragma unroll
-          for (int v = 0; v < 52; ++v) share[li][v] = 0.0f;
-          const float4* dq = reinterpret_cast<const float4*>(tb->dctq);
-          static_for<0, kDctQuads>([&](auto ic) {
-            constexpr int i = decltype(ic)::value;
-            const float4 q = dq[i * 32 + lane];
-            const float qc[4] = {q.x, q.y, q.z, q.w};
-            static_for<0, 4>([&](auto cc) {
-              constexpr int c = decltype(cc)::value;
-              constexpr int s = (4 * i + c) / kMfcc, k = (4 * i + c) % kMfcc;
+          for (int j = 0; j < 4; ++j)
   #pragma unroll
-              for (int j = 0; j < 4; ++j) share[li][j * kMfcc + k] = fmaf(db[j][s], qc[c], share[li][j * kMfcc + k]);
-            });
-          });
+            for (int s = 0; s < 4; ++s) {
+              const float d = dbs[li][j][s];
+              const float hi = int_as_float(float_as_int(d) & (int)0xFFFFE000);     // 11 significant bits: exact in fp16
+              dbw[j * kDbRow + 32 * s + lane] = h2_pack(hi, d - hi);
+            }
         });
         env.wsync();
         if (pass == 0) {
@@ -639,41 +643,61 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
             });
           }
         }
-        env.lanes([&](int lane, int li) {
-  #pragma unroll
-          for (int v = 0; v < 52; ++v) fbuf[v * 33 + lane] = share[li][v];
-        });
         env.wsync();
-        env.lanes([&](int lane, int li) {
+        // MFCC[k][frame] = sum_m dct[m][k] dB[frame][m] as 8 k-steps of mma.sync m16n8k16 (fp16 operands, fp32 accumulate):
+        // A = DCT fragments (rows = 13 coefficients padded to 16, constant, shared memory), B = the quad's dB values
+        // (rows = 16 mel filters of the k-step, columns = frames: lane (g, t) supplies frame g % 4).  Both operands are
+        // split hi + lo and the three significant products are issued (hi hi + lo hi + hi lo): ~2^-21 relative.
+        {
+          float acc[S][4];
+          u32 bh[S][2], bl[S][2], ah[S][4], al[S][4];
+          env.lanes([&](int lane, int li) { (void)lane; acc[li][0] = acc[li][1] = acc[li][2] = acc[li][3] = 0.0f; });
+          const u32* dbw = reinterpret_cast<const u32*>(fbuf);
   #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int v = lane + 32 * half;
-            float a = 0.0f;
-            if (v < 52) {
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) a += fbuf[v * 33 + j];
-            }
-            asum[li][half] = a;
+          for (int kap = 0; kap < 8; ++kap) {
+            env.lanes([&](int lane, int li) {
+              const int g = lane >> 2, tq = lane & 3;
+              u32 w0[2], w1[2];
+              env.lds2(w0, dbw + (g & 3) * kDbRow + 16 * kap + 2 * tq);
+              env.lds2(w1, dbw + (g & 3) * kDbRow + 16 * kap + 2 * tq + 8);
+              bh[li][0] = h2_lows(w0[0], w0[1]); bl[li][0] = h2_highs(w0[0], w0[1]);
+              bh[li][1] = h2_lows(w1[0], w1[1]); bl[li][1] = h2_highs(w1[0], w1[1]);
+              env.lds4(ah[li], tb->dct_frag[0][kap][lane]);
+              env.lds4(al[li], tb->dct_frag[1][kap][lane]);
+            });
+            env.mma_f32(MSA_R(acc[li_]), MSA_R(ah[li_]), MSA_R(bh[li_]));
+            env.mma_f32(MSA_R(acc[li_]), MSA_R(ah[li_]), MSA_R(bl[li_]));
+            env.mma_f32(MSA_R(acc[li_]), MSA_R(al[li_]), MSA_R(bh[li_]));
           }
-        });
-        env.wsync();
+          env.wsync();
+          // lane (g, t < 2) holds coefficients g and g + 8 of frames 2 t and 2 t + 1
+          env.lanes([&](int lane, int li) {
+            const int g = lane >> 2, tq = lane & 3;
+            if (tq < 2) {
+  #pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int fr = m0 + 2 * tq + e;
+                if (fr < nFm) {
+                  mfl[(fr - mf_begin) * kMfcc + g] = acc[li][e];
+                  if (g + 8 < kMfcc) mfl[(fr - mf_begin) * kMfcc + g + 8] = acc[li][2 + e];
+                }
+              }
+            }
+          });
+          env.wsync();
+        }
         if (pass == 1) {                                             // recomputed quad (no scratch table): add the delta DCT
           delta_dct();
           env.lanes([&](int lane, int li) {
-            (void)lane;
-            asum[li][0] += casum[li][0];
-            asum[li][1] += casum[li][1];
-          });
-        }
-        env.lanes([&](int lane, int li) {
   #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int v = lane + 32 * half;
-            const int fr = m0 + v / kMfcc;
-            if (v < 52 && fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] = asum[li][half];
-          }
-        });
-        env.wsync();
+            for (int half = 0; half < 2; ++half) {
+              const int v = lane + 32 * half;
+              const int fr = m0 + v / kMfcc;
+              if (v < 52 && fr < nFm) mfl[(fr - mf_begin) * kMfcc + v % kMfcc] += casum[li][half];
+            }
+          });
+          env.wsync();
+        }
       }
     const int ops[2] = {kOpMax, kOpMin};
     block_reduce<2>(env, wred, rout, ops, [&](int li, int k) { return k == 0 ? (double)dmax[li] : (double)dmin[li]; });
@@ -726,7 +750,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               const float d = int_as_float(ce.y);
               if (d < thr) {
                 const int m = ce.x & 127, j = (ce.x >> 7) & 3, q = (m >> 5) * kMfcc + lane;
-                const float w = tb->dctq[((q >> 2) * 32 + (m & 31)) * 4 + (q & 3)];
+                const float w = env.ldf(P.tab->dctq + ((q >> 2) * 32 + (m & 31)) * 4 + (q & 3));
                 float* o = fb + (j * kMfcc + lane) * 33 + (m & 31);
                 *o = fmaf(thr - d, w, *o);
               }

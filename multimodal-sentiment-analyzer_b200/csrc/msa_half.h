@@ -61,6 +61,14 @@ MSA_FN u32 h2_pack(float lo, float hi) { return (u32)h_from_f32(lo) | ((u32)h_fr
 MSA_FN float h2_lo(u32 v) { return (float)h_of((uint16_t)(v & 0xffffu)); }
 MSA_FN float h2_hi(u32 v) { return (float)h_of((uint16_t)(v >> 16)); }
 #endif
+// {lo(a), lo(b)} and {hi(a), hi(b)}: regroup two words that each hold one value's (hi, lo) fp16 parts
+#if defined(__CUDA_ARCH__)
+MSA_FN u32 h2_lows(u32 a, u32 b) { return __byte_perm(a, b, 0x5410); }
+MSA_FN u32 h2_highs(u32 a, u32 b) { return __byte_perm(a, b, 0x7632); }
+#else
+MSA_FN u32 h2_lows(u32 a, u32 b) { return (a & 0xffffu) | (b << 16); }
+MSA_FN u32 h2_highs(u32 a, u32 b) { return (a >> 16) | (b & 0xffff0000u); }
+#endif
 MSA_FN u32 h2_neg(u32 a) { return a ^ 0x80008000u; }
 MSA_FN u32 h2_abs(u32 a) { return a & 0x7fff7fffu; }
 

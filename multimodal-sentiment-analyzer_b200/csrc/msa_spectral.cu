@@ -28,7 +28,7 @@ constexpr int kSpRow = 25;                               // row stride (complex 
 constexpr int kSpBins = 208;                             // 201 bins + zero pad for the mel trips
 
 struct SpectralTables {                                  // the slice of SmemTables this kernel needs
-  float tw400[2 * 15 * 32];
+  float tw400[2 * 15 * 25 + 2];
   float win400[kNfftM];
   float mel_w[kMelTrips * 32];
   uint16_t mel_lo[4 * 32];
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kSpWarps * 32) spectral_kernel(const InT* __re
   c32* tile = tiles[warp];
   const c32* tw = reinterpret_cast<const c32*>(tab.tw400);
   // pass A: lane n2 < 25 takes the 16 stride-25 samples of frame t - 1 (real part) and frame t (imaginary part)
+  bool nz_a = false, nz_b = false;                       // does the frame hold any non-zero sample?
   if (lane < 25) {
     const int sb = kHopM * t - kNfftM / 2;               // first sample of frame t
     c32 z[16];
@@ -69,13 +70,20 @@ __global__ void __launch_bounds__(kSpWarps * 32) spectral_kernel(const InT* __re
     for (int n1 = 0; n1 < 16; ++n1) {
       const float w = tab.win400[25 * n1 + lane];
       const float a = (t > 0) ? xr(sb - kHopM + 25 * n1 + lane) : 0.0f;
-      z[n1] = c32{w * a, w * xr(sb + 25 * n1 + lane)};
+      const float b = xr(sb + 25 * n1 + lane);
+      nz_a = nz_a || (a != 0.0f);
+      nz_b = nz_b || (b != 0.0f);
+      z[n1] = c32{w * a, w * b};
     }
     dft16<false>(z);
     tile[lane] = z[0];
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) tile[k1 * kSpRow + lane] = cmul(z[k1], tw[(k1 - 1) * 32 + lane]);
+    for (int k1 = 1; k1 < 16; ++k1) tile[k1 * kSpRow + lane] = cmul(z[k1], tw[(k1 - 1) * 25 + lane]);
   }
+  // a frame of digital silence has an exactly zero spectrum (centroid 0 / 0 = NaN like torchaudio); separated from its
+  // packed partner it would come out as that partner's rounding residue instead
+  nz_a = __any_sync(0xffffffffu, nz_a);
+  nz_b = __any_sync(0xffffffffu, nz_b);
   __syncwarp();
   if (lane < 16) {                                       // pass B: row k1 -> Z[k1 + 16 k2]
     c32* row = tile + lane * kSpRow;
@@ -98,8 +106,8 @@ __global__ void __launch_bounds__(kSpWarps * 32) spectral_kernel(const InT* __re
       const int kk = (k == 0) ? 0 : kNfftM - k;
       const c32 zk = tile[(k & 15) * kSpRow + (k >> 4)], zn = tile[(kk & 15) * kSpRow + (kk >> 4)];
       const c32 sm = add_conj(zk, zn), df = sub_conj(zk, zn);
-      pa[i] = 0.25f * fmaf(sm.x, sm.x, sm.y * sm.y);
-      pb[i] = 0.25f * fmaf(df.x, df.x, df.y * df.y);
+      pa[i] = nz_a ? 0.25f * fmaf(sm.x, sm.x, sm.y * sm.y) : 0.0f;
+      pb[i] = nz_b ? 0.25f * fmaf(df.x, df.x, df.y * df.y) : 0.0f;
     }
   }
   __syncwarp();                                          // every lane has read the tile: its memory now holds the rows
@@ -182,7 +190,7 @@ static int get_spectral_tables(const SpectralTables** out) {
     static FeatureTables ft;
     static SpectralTables host;
     build_feature_tables(ft);
-    std::memcpy(host.tw400, ft.s.tw400, sizeof(host.tw400));
+    std::memcpy(host.tw400, ft.s.tw400, sizeof(ft.s.tw400));
     std::memcpy(host.win400, ft.s.win400, sizeof(host.win400));
     std::memcpy(host.mel_w, ft.s.mel_w, sizeof(host.mel_w));
     std::memcpy(host.mel_lo, ft.s.mel_lo, sizeof(host.mel_lo));

@@ -73,10 +73,14 @@ struct alignas(16) PitchRegTables {       // read once per work item into regist
 
 // The part every CTA stages in shared memory (copied as 16-byte words: keep the size a multiple of 16).
 struct alignas(16) SmemTables {
-  float tw400[2 * 15 * 32];       // [(k1-1)*32 + n2] = W_400^(n2 k1), n2 < 25
+  float tw400[2 * 15 * 25];       // [(k1-1)*25 + n2] = W_400^(n2 k1) as (cos, -sin), n2 < 25 (8-byte entries)
+  float tw400_pad[2];             // keeps the next member 16-byte aligned
   float win400[kNfftM];
   float mel_w[kMelTrips * 32];    // [(trip offset of slot s + p)*32 + lane], zero padded
-  float dctq[kDctQuads * 32 * 4]; // float4 [i*32 + lane]: flattened (slot, k) = divmod(4 i + c, 13); 0 for empty filters
+  // the 13 x 128 DCT as mma.sync m16n8k16 A fragments (rows = coefficient k, padded to 16; K = mel filter), split into
+  // fp16 hi + lo parts: [hi | lo][k-step kappa][lane][4 registers]; rows of EMPTY mel filters are zero (they enter through
+  // dct_dead).  lane (g, t): {D[g][16 kappa + 2 t], D[g][.. + 1]}, {D[g + 8][..]}, {D[g][16 kappa + 2 t + 8], ..}, {D[g + 8][..]}
+  uint32_t dct_frag[2][8][32][4];
   float dct_dead[16];             // sum over the empty filters of dct[m][k]
   uint16_t mel_lo[4 * 32];        // first bin of filter 32 s + lane (0 for the empty filters)
   uint16_t mel_dead[4 * 32];      // 1 where the filter has no non-zero weight
@@ -88,6 +92,8 @@ static_assert(sizeof(SmemTables) % 16 == 0, "SmemTables is copied as int4");
 struct FeatureTables {
   SmemTables s;
   float dct[kMels * 16];          // plain [m][k] table (tests / reference restatement)
+  float dctq[kDctQuads * 32 * 4]; // float4 [i*32 + lane]: flattened (slot, k) = divmod(4 i + c, 13); 0 for empty filters (the
+                                  // clamp-delta paths read it from global memory: they are rare)
   PitchRegTables pr;
   int mel_nnz;
   int pad[3];
@@ -100,9 +106,11 @@ inline int build_feature_tables(FeatureTables& ft) {
   for (int n = 0; n < kNfftM; ++n) t.win400[n] = (float)(0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftM));
   for (int k1 = 1; k1 < 16; ++k1)
     for (int n2 = 0; n2 < 32; ++n2) {
-      const double b = 2.0 * PI * (double)((n2 < 25 ? n2 : 0) * k1) / 400.0;
-      t.tw400[2 * ((k1 - 1) * 32 + n2)] = (float)std::cos(b);
-      t.tw400[2 * ((k1 - 1) * 32 + n2) + 1] = (float)(-std::sin(b));
+      if (n2 < 25) {
+        const double b = 2.0 * PI * (double)(n2 * k1) / 400.0;
+        t.tw400[2 * ((k1 - 1) * 25 + n2)] = (float)std::cos(b);
+        t.tw400[2 * ((k1 - 1) * 25 + n2) + 1] = (float)(-std::sin(b));
+      }
     }
   // DCT-II ortho (torchaudio.functional.create_dct(13, 128, "ortho"))
   for (int m = 0; m < kMels; ++m)
@@ -142,10 +150,39 @@ inline int build_feature_tables(FeatureTables& ft) {
     for (int k = 0; k < kMfcc; ++k) {
       const int e = s * kMfcc + k;                       // flattened (slot, k)
       if (cnt == 0) t.dct_dead[k] += ft.dct[m * 16 + k];
-      else t.dctq[((e / 4) * 32 + lane) * 4 + (e % 4)] = ft.dct[m * 16 + k];
+      else ft.dctq[((e / 4) * 32 + lane) * 4 + (e % 4)] = ft.dct[m * 16 + k];
     }
   }
   ft.mel_nnz = nnz;
+  // ---- DCT fragments (fp16 hi + lo of every entry: hi = fp16(v), lo = fp16(v - hi))
+  for (int kap = 0; kap < 8; ++kap)
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, tq = lane & 3;
+      auto val = [&](int k, int m) -> float {
+        if (k >= kMfcc) return 0.0f;
+        if (t.mel_dead[(m / 32) * 32 + (m % 32)]) return 0.0f;
+        return ft.dct[m * 16 + k];
+      };
+      auto split = [&](float v, int part) -> uint16_t {
+        const uint16_t hb = f32_to_f16_bits(v);
+        if (part == 0) return hb;
+        // value of hb as float
+        const uint32_t sign = (hb & 0x8000u) << 16, e = (hb >> 10) & 0x1fu, mant = hb & 0x3ffu;
+        float hv;
+        if (e == 0) hv = std::ldexp((float)mant, -24);
+        else hv = std::ldexp((float)(mant | 0x400u), (int)e - 25);
+        if (sign) hv = -hv;
+        return f32_to_f16_bits(v - hv);
+      };
+      for (int part = 0; part < 2; ++part) {
+        uint32_t* o = t.dct_frag[part][kap][lane];
+        const int m0 = 16 * kap + 2 * tq;
+        o[0] = (uint32_t)split(val(g, m0), part) | ((uint32_t)split(val(g, m0 + 1), part) << 16);
+        o[1] = (uint32_t)split(val(g + 8, m0), part) | ((uint32_t)split(val(g + 8, m0 + 1), part) << 16);
+        o[2] = (uint32_t)split(val(g, m0 + 8), part) | ((uint32_t)split(val(g, m0 + 9), part) << 16);
+        o[3] = (uint32_t)split(val(g + 8, m0 + 8), part) | ((uint32_t)split(val(g + 8, m0 + 9), part) << 16);
+      }
+    }
   // ---- fragments of the tensor-core STFT-512 round trip
   auto hann = [&](int n) { return 0.5 - 0.5 * std::cos(2.0 * PI * n / kNfftP); };
   for (int lane = 0; lane < 32; ++lane) {

@@ -95,6 +95,33 @@ struct CpuEnv {
       d[1] = msa::h2_pack(Dm[g + 8][2 * t], Dm[g + 8][2 * t + 1]);
     }
   }
+  template <class D, class A, class B> void mma_f32(D dg, A ag, B bg) {
+    float Am[16][16], Bm[16][8], Dm[16][8];
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      const uint32_t* a = ag(l);
+      const uint32_t* b = bg(l);
+      const float* c = dg(l);
+      for (int e = 0; e < 2; ++e) {
+        Am[g][2 * t + e] = h16(a[0], e); Am[g + 8][2 * t + e] = h16(a[1], e);
+        Am[g][2 * t + 8 + e] = h16(a[2], e); Am[g + 8][2 * t + 8 + e] = h16(a[3], e);
+        Bm[2 * t + e][g] = h16(b[0], e); Bm[2 * t + 8 + e][g] = h16(b[1], e);
+        Dm[g][2 * t + e] = c[e]; Dm[g + 8][2 * t + e] = c[2 + e];
+      }
+    }
+    for (int i = 0; i < 16; ++i)
+      for (int j = 0; j < 8; ++j) {
+        double s = Dm[i][j];                       // the tensor core adds the 16 exact products and the accumulator with
+        for (int k = 0; k < 16; ++k) s += (double)Am[i][k] * (double)Bm[k][j];   // extra internal bits and rounds once
+        Dm[i][j] = (float)s;
+      }
+    for (int l = 0; l < 32; ++l) {
+      const int g = l >> 2, t = l & 3;
+      float* d = dg(l);
+      for (int e = 0; e < 2; ++e) { d[e] = Dm[g][2 * t + e]; d[2 + e] = Dm[g + 8][2 * t + e]; }
+    }
+  }
+  float ldf(const float* p) { return *p; }
   template <class R, class P> void ldsm4t(R rg, P pg) {
     for (int m = 0; m < 4; ++m) {
       uint16_t tile[8][8];
