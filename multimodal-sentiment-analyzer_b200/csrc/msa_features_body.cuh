@@ -649,9 +649,13 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         // (rows = 16 mel filters of the k-step, columns = frames: lane (g, t) supplies frame g % 4).  Both operands are
         // split hi + lo and the three significant products are issued (hi hi + lo hi + hi lo): ~2^-21 relative.
         {
-          float acc[S][4];
+          float acc[S][4], acc1[S][4], acc2[S][4];                       // three independent accumulation chains
           u32 bh[S][2], bl[S][2], ah[S][4], al[S][4];
-          env.lanes([&](int lane, int li) { (void)lane; acc[li][0] = acc[li][1] = acc[li][2] = acc[li][3] = 0.0f; });
+          env.lanes([&](int lane, int li) {
+            (void)lane;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) acc[li][i] = acc1[li][i] = acc2[li][i] = 0.0f;
+          });
           const u32* dbw = reinterpret_cast<const u32*>(fbuf);
   #pragma unroll
           for (int kap = 0; kap < 8; ++kap) {
@@ -666,9 +670,14 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
               env.lds4(al[li], tb->dct_frag[1][kap][lane]);
             });
             env.mma_f32(MSA_R(acc[li_]), MSA_R(ah[li_]), MSA_R(bh[li_]));
-            env.mma_f32(MSA_R(acc[li_]), MSA_R(ah[li_]), MSA_R(bl[li_]));
-            env.mma_f32(MSA_R(acc[li_]), MSA_R(al[li_]), MSA_R(bh[li_]));
+            env.mma_f32(MSA_R(acc1[li_]), MSA_R(ah[li_]), MSA_R(bl[li_]));
+            env.mma_f32(MSA_R(acc2[li_]), MSA_R(al[li_]), MSA_R(bh[li_]));
           }
+          env.lanes([&](int lane, int li) {
+            (void)lane;
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) acc[li][i] += acc1[li][i] + acc2[li][i];     // the two correction terms first
+          });
           env.wsync();
           // lane (g, t < 2) holds coefficients g and g + 8 of frames 2 t and 2 t + 1
           env.lanes([&](int lane, int li) {

@@ -78,40 +78,53 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
     for (int j = 0; j < 4; ++j) { wa[li][j][0] = env.ldu(&gt->wa[j][lane][0]); wa[li][j][1] = env.ldu(&gt->wa[j][lane][1]); }
   });
   u32 acc[S][4][2];                                                     // overlap-add ring: rows rho = g (0) / g + 8 (1), columns 8 j + 2 t
-  for (int i = 0; i < S; ++i)
+  // the residual's sums stay in fp32 for the warp's whole run (a few hundred terms of similar size per lane; the feature
+  // built from them is rounding residue by construction) and reach the fp64 block reduction once: the fp64 pipe of this
+  // chip is narrow, and three DADDs per pair of frames showed up as 4 % of the kernel's stall samples
+  float rs1[S], rs2[S], rmx[S];
+  int rcnt[S];
+  for (int i = 0; i < S; ++i) {
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0u;
+    rs1[i] = rs2[i] = rmx[i] = 0.0f;
+    rcnt[i] = 0;
+  }
 
-  // ---- staging: 512 padded positions per step, 16 per lane, as fp16 into the ring
+  // ---- staging: 512 padded positions per step, 16 per lane, as fp16 into the ring.  A step is split in two: the global
+  // loads are issued at the top of a quad and their conversion + stores run at its end, one quad before the data is
+  // needed, so the L2 / HBM latency hides behind a quad's worth of matrix products (this kernel leaves no room for L1).
   int staged = kHopP * 4 * wq_first;                                    // first padded position not yet in the ring
-  auto stage_chunk = [&]() {
+  float sv[S][16];
+  auto stage_load = [&]() {
     env.lanes([&](int lane, int li) {
-      (void)li;
       const int p = staged + 16 * lane, t0 = p - kNfftP / 2;
-      float v[16];
       if (t0 >= 0 && t0 + 16 <= T) {
-        env.ld16(x, t0, v);
+        env.ld16(x, t0, sv[li]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = xr(t0 + i);
+        for (int i = 0; i < 16; ++i) sv[li][i] = xr(t0 + i);
       }
+    });
+  };
+  auto stage_store = [&]() {
+    env.lanes([&](int lane, int li) {
+      const int p = staged + 16 * lane;
       u32 w[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) w[i] = h2_pack(v[2 * i], v[2 * i + 1]);
+      for (int i = 0; i < 8; ++i) w[i] = h2_pack(sv[li][2 * i], sv[li][2 * i + 1]);
       env.st8(ring + ring_off(p), w);                                   // two chunks of one row
       env.st8(ring + ring_off(p + 8), w + 4);
-      // the chunk after this one is requested into L1 now (one 128-byte line per lane), so that its loads, one quad
-      // from now, do not wait for L2 / HBM
-      constexpr int kPerLine = 128 / (int)sizeof(InT);
-      const int tn = staged + 512 - kNfftP / 2 + lane * kPerLine;
-      if (lane * kPerLine < 512 && tn >= 0 && tn < T) env.prefetch_l1(x + tn);
     });
     staged += 512;
   };
+  const int stage_end = kHopP * (4 * wq_end) + 896;                     // nothing behind the run's last frame is needed
+  // the first quad of the run needs two chunks at once
+  while (staged < kHopP * (4 * wq_first) + 896) { stage_load(); stage_store(); }
 
   for (int quad = wq_first; quad < wq_end; ++quad) {
     const int f0 = 4 * quad;
-    // this quad reads positions [128 f0, 128 f0 + 896); the chunk behind it is requested one quad ahead
-    while (staged < kHopP * f0 + 896 + 512 && staged < kHopP * (4 * wq_end) + 896) stage_chunk();
+    // this quad reads positions [128 f0, 128 f0 + 896), all in the ring; the chunk the NEXT quad adds is requested now
+    const bool more = staged < kHopP * f0 + 896 + 512 && staged < stage_end;
+    if (more) stage_load();
     env.wsync();
     const bool owned = quad >= wq_begin;
 
@@ -356,12 +369,17 @@ MSA_KFN void pitch_tc(Env& env, const InT* x, int T, int q_begin, int q_end, uin
                 }
               }
           }
-          ps[li] += (double)s1; pq[li] += (double)s2; pn[li] += (double)cnt;
-          pmax[li] = fmaxf(pmax[li], mx);
+          rs1[li] += s1; rs2[li] += s2; rcnt[li] += cnt;
+          rmx[li] = fmaxf(rmx[li], mx);
         });
       }
     });
-    env.wsync();                                                        // the ring positions behind this quad may be overwritten
+    if (more) stage_store();                                            // (the ring keeps 2048 positions: nothing live is overwritten)
+    env.wsync();
+  }
+  for (int i = 0; i < S; ++i) {
+    ps[i] += (double)rs1[i]; pq[i] += (double)rs2[i]; pn[i] += (double)rcnt[i];
+    pmax[i] = fmaxf(pmax[i], rmx[i]);
   }
 }
 
