@@ -879,44 +879,34 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
     block_reduce<2>(env, wred, rout, ops2, [&](int li, int k) { return k == 0 ? gs[li] : bs[li]; });
     const double gq = rout[0], bq = rout[1];
 
-    // The row: warp 0, one raw feature / LayerNorm entry / output word per lane.  Every lane forms the segment-level
-    // scalars itself (uniform: the same operations in the same order a single thread would run), while the per-entry
-    // work (two fp64 divisions per MFCC coefficient, the LayerNorm entries, nan_to_num, the stores) is spread over
-    // the lanes.  (A single-thread version of this block took ~20 us per segment, 7 % of a CTA's life, during which
-    // the CTA's other warps idle at the last barrier.)
+    // The row.  The segment-level scalars fall into three independent groups, each a serial chain of fp64 divisions and
+    // square roots, so THREE warps form them side by side (warp 0: emotion, "pitch", intensity, speech rate, rhythm;
+    // warp 1: timbre and clarity; warp 2: SNR and consistency), one raw feature per lane where a feature has 13 entries;
+    // warp 0 then runs the LayerNorm, nan_to_num and the stores, one entry per lane.  Every scalar is computed by the
+    // same operations in the same order as a single thread would (the bits do not depend on this split).  (As one
+    // warp's chain this block took ~20 us per segment, 8 % of a CTA's life, with the CTA's other warps parked at the
+    // last barrier: profiles/r2_v202_features_ncu_full_B1024.txt.)
+    float* raw = reinterpret_cast<float*>(wred);            // [0:27] raw features
+    double* qd = rout;                                       // [0] snr, [1] clarity, [2] consistency (python floats = doubles),
+                                                             // [4:11] diagnostics of the detail record
+    const float* emo = P.emo8 ? P.emo8 + (size_t)seg * 8 : nullptr;
+    env.sync();                                              // wred / rout are free (the last block reduction has been read)
     if (env.warp == 0) {
-      float* raw = reinterpret_cast<float*>(wred);          // raw27 staged for the LayerNorm sums
-      const float* emo = P.emo8 ? P.emo8 + (size_t)seg * 8 : nullptr;
-      float q4s[S][4], dg[S][7];
       env.lanes([&](int lane, int li) {
+        (void)li;
         const double NaN = nan("");
-        // merge the ranks' partial moments in rank order
-        double p_n = part->p_n, p_sum = part->p_sum, p_sumsq = part->p_sumsq, e_total = part->e_total, e_noise = part->e_noise;
-        double mf_sumsq = part->mf_sumsq, mf_abs_lo = part->mf_abs_lo, mf_abs_hi = part->mf_abs_hi;
+        double p_n = part->p_n, p_sum = part->p_sum, p_sumsq = part->p_sumsq, e_total = part->e_total;
         float p_max = part->p_max;
-        int mf_frames = part->mf_frames;
 #pragma unroll 1
         for (int rr = 1; rr < NR; ++rr) {
           const Partials* rp = gathered + rr;
-          mf_sumsq += rp->mf_sumsq; mf_abs_lo += rp->mf_abs_lo; mf_abs_hi += rp->mf_abs_hi;
-          p_n += rp->p_n; p_sum += rp->p_sum; p_sumsq += rp->p_sumsq;
-          e_total += rp->e_total; e_noise += rp->e_noise;
+          p_n += rp->p_n; p_sum += rp->p_sum; p_sumsq += rp->p_sumsq; e_total += rp->e_total;
           p_max = fmaxf(p_max, rp->p_max);
-          mf_frames += rp->mf_frames;
-        }
-        double ssum = 0.0, mf_mine = 0.0;                     // sum of all coefficient sums; the lane's own coefficient
-#pragma unroll 1
-        for (int k = 0; k < kMfcc; ++k) {
-          double t = part->mf_sum[k];
-#pragma unroll 1
-          for (int rr = 1; rr < NR; ++rr) t += gathered[rr].mf_sum[k];
-          ssum += t;
-          if (k == lane - 10) mf_mine = t;
         }
         float mine = 0.0f;                                    // raw[lane]
         if (lane < 8) mine = emo ? emo[lane] : 0.125f;
         // pitch: mean of the z-scored residual. mu and sigma are fp32 tensors in the reference, so the
-        // value is the rounding residue of mu; the residual itself is fp32 FFT noise (~1e-8).
+        // value is the rounding residue of mu; the residual itself is fp16 rounding noise of the tensor-core round trip.
         double p_mean = 0.0, p_std = 0.0;
         if (p_n > 1.0) {
           p_mean = p_sum / p_n;
@@ -927,17 +917,6 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         }
         // intensity: (e - mean(e)) / (std(e) + 1e-6) over ONE channel: std of one element is NaN
         if (lane == 9) mine = (P.flags & kFlagStrictNan) ? (float)NaN : 0.0f;
-        // timbre
-        double clarity = 0.0;
-        if (mf_frames > 0) {
-          const double n = (double)mf_frames * kMfcc;
-          const double mu = ssum / n;
-          const double var = (n > 1.0) ? (mf_sumsq - ssum * mu) / (n - 1.0) : NaN;
-          const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : NaN));
-          if (lane >= 10 && lane < 10 + kMfcc) mine = (float)((mf_mine / mf_frames - mu) / (sd + 1e-6));
-          const double hi_m = mf_abs_hi / (7.0 * mf_frames), lo_m = mf_abs_lo / (6.0 * mf_frames);
-          clarity = py_clip01((double)((float)hi_m / ((float)lo_m + 1e-6f)));
-        }
         // speech rate (mono): energy > 0.1 * energy in fp32
         if (lane == 23) {
           const float e = (float)e_total;
@@ -949,6 +928,56 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           if (lane == 25) mine = (nG > 1) ? (float)sqrt(gq / (nG - 1)) : (float)NaN;
           if (lane == 26) mine = (float)((double)nG / (double)kSampleRate);
         }
+        if (lane < 10 || (lane >= 23 && lane < 27)) raw[lane] = mine;
+        if (lane == 0) { qd[4] = p_mean; qd[5] = p_std; qd[6] = (double)p_max; qd[7] = e_total; qd[10] = p_n; }
+      });
+    }
+    // groups 1 and 2 run on warps 1 and 2 when the CTA has them, else on warp 0 after its own group
+    const int w1 = (NW > 1) ? 1 : 0, w2 = (NW > 2) ? 2 : 0;
+    if (env.warp == w1) {
+      env.lanes([&](int lane, int li) {
+        (void)li;
+        const double NaN = nan("");
+        double mf_sumsq = part->mf_sumsq, mf_abs_lo = part->mf_abs_lo, mf_abs_hi = part->mf_abs_hi;
+        int mf_frames = part->mf_frames;
+#pragma unroll 1
+        for (int rr = 1; rr < NR; ++rr) {
+          const Partials* rp = gathered + rr;
+          mf_sumsq += rp->mf_sumsq; mf_abs_lo += rp->mf_abs_lo; mf_abs_hi += rp->mf_abs_hi;
+          mf_frames += rp->mf_frames;
+        }
+        double ssum = 0.0, mf_mine = 0.0;                     // sum of all coefficient sums; the lane's own coefficient
+#pragma unroll 1
+        for (int k = 0; k < kMfcc; ++k) {
+          double t = part->mf_sum[k];
+#pragma unroll 1
+          for (int rr = 1; rr < NR; ++rr) t += gathered[rr].mf_sum[k];
+          ssum += t;
+          if (k == lane - 10) mf_mine = t;
+        }
+        float mine = 0.0f;
+        double clarity = 0.0;
+        if (mf_frames > 0) {
+          const double n = (double)mf_frames * kMfcc;
+          const double mu = ssum / n;
+          const double var = (n > 1.0) ? (mf_sumsq - ssum * mu) / (n - 1.0) : NaN;
+          const double sd = sqrt(var > 0.0 ? var : (var == var ? 0.0 : NaN));
+          if (lane >= 10 && lane < 10 + kMfcc) mine = (float)((mf_mine / mf_frames - mu) / (sd + 1e-6));
+          const double hi_m = mf_abs_hi / (7.0 * mf_frames), lo_m = mf_abs_lo / (6.0 * mf_frames);
+          clarity = py_clip01((double)((float)hi_m / ((float)lo_m + 1e-6f)));
+        }
+        if (!(P.parts & kPartMfcc)) clarity = 0.0;
+        if (lane >= 10 && lane < 10 + kMfcc) raw[lane] = mine;
+        if (lane == 0) { qd[1] = clarity; qd[9] = (double)mf_frames; }
+      });
+    }
+    if (env.warp == w2) {
+      env.lanes([&](int lane, int li) {
+        (void)li;
+        const double NaN = nan("");
+        double e_total = part->e_total, e_noise = part->e_noise;
+#pragma unroll 1
+        for (int rr = 1; rr < NR; ++rr) { e_total += gathered[rr].e_total; e_noise += gathered[rr].e_noise; }
         // quality scalars (python floats in the reference: double arithmetic on fp32 .item() values)
         double snr = 0.0, consistency = 0.0;
         if (P.noise_n > 0 && (P.parts & kPartWave)) {
@@ -962,15 +991,15 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
           const double cv = (double)(sd / ((float)bmean + 1e-6f));
           consistency = 1.0 - ((1.0 < cv) ? 1.0 : cv);   // python min(cv, 1.0): NaN stays NaN
         }
-        if (!(P.parts & kPartMfcc)) clarity = 0.0;
-        const double quality = 0.4 * snr + 0.3 * clarity + 0.3 * consistency;
-        q4s[li][0] = (float)quality; q4s[li][1] = (float)snr; q4s[li][2] = (float)clarity; q4s[li][3] = (float)consistency;
-        dg[li][0] = (float)p_mean; dg[li][1] = (float)p_std; dg[li][2] = p_max; dg[li][3] = (float)e_total;
-        dg[li][4] = (float)e_noise; dg[li][5] = (float)mf_frames; dg[li][6] = (float)p_n;
-        if (lane < 27) raw[lane] = mine;
+        if (lane == 0) { qd[0] = snr; qd[2] = consistency; qd[8] = e_noise; }
       });
-      env.wsync();
+    }
+    env.sync();
+    if (env.warp == 0) {
       env.lanes([&](int lane, int li) {
+        (void)li;
+        const double quality = 0.4 * qd[0] + 0.3 * qd[1] + 0.3 * qd[2];
+        const float q4[4] = {(float)quality, (float)qd[0], (float)qd[1], (float)qd[2]};
         // AudioFeatureNormalizer: pad 27 -> 31 with zeros, LayerNorm(31) (gamma 1, beta 0, eps 1e-5, biased var)
         double m = 0.0;
 #pragma unroll 1
@@ -985,7 +1014,7 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         const float lnv = (float)(((double)mine - m) * rs);
         // fusion input row: LN slices ++ quality, torch.nan_to_num(nan=0.0) (+-inf -> +-FLT_MAX)
         if (lane < 31) {
-          float o = (lane < 27) ? lnv : q4s[li][lane - 27];
+          float o = (lane < 27) ? lnv : q4[lane - 27];
           if (o != o) o = 0.0f;
           else if (o > 3.4028234663852886e38f) o = 3.4028234663852886e38f;
           else if (o < -3.4028234663852886e38f) o = -3.4028234663852886e38f;
@@ -994,13 +1023,13 @@ MSA_KFN void features_cta(Env& env, const FeatParams& P, unsigned char* smem) {
         if (P.detail) {
           float* d = P.detail + (size_t)seg * kDetailStride;
           if (lane < 27) d[lane] = mine;
-          if (lane < 4) d[27 + lane] = q4s[li][lane];
+          if (lane < 4) d[27 + lane] = q4[lane];
           if (lane < 31) d[32 + lane] = lnv;
           if (lane == 31) { d[31] = 0.0f; d[63] = 0.0f; }
           if (lane == 0) {
-            d[64] = gmax; d[65] = dg[li][0]; d[66] = dg[li][1]; d[67] = dg[li][2];
-            d[68] = dg[li][3]; d[69] = dg[li][4]; d[70] = dg[li][5]; d[71] = (float)nG;
-            d[72] = dg[li][6]; d[73] = (float)nBk; d[74] = (float)nA;
+            d[64] = gmax; d[65] = (float)qd[4]; d[66] = (float)qd[5]; d[67] = (float)qd[6];
+            d[68] = (float)qd[7]; d[69] = (float)qd[8]; d[70] = (float)qd[9]; d[71] = (float)nG;
+            d[72] = (float)qd[10]; d[73] = (float)nBk; d[74] = (float)nA;
             d[75] = slow ? 1.0f : 0.0f; d[76] = gmin; d[77] = cand; d[78] = fix ? 1.0f : 0.0f;
             d[79] = 0.0f;
           }
