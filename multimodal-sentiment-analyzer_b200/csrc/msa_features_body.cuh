@@ -55,7 +55,10 @@ constexpr int kRow512 = 33, kRow400 = 25;        // row strides (complex words) 
 constexpr int kFftHalf = 16 * kRow512;           // spacing (complex words) of the two power-spectrum row pairs in a warp's buffer
 constexpr int kGroup = 640;                      // wave-statistics unit: 8 energy atoms, 5 float4 per lane
 constexpr int kRedSlots = 16;
-constexpr int kK1Groups = 2;                     // load groups in flight per warp in the wave-statistics phase (160 floats of scratch each; 4 in flight measured no faster)
+#ifndef MSA_K1_GROUPS
+#define MSA_K1_GROUPS 2
+#endif
+constexpr int kK1Groups = MSA_K1_GROUPS;                     // load groups in flight per warp in the wave-statistics phase (160 floats of scratch each; 4 in flight measured no faster)
 constexpr int kTileM = 16 * kRow400;             // one MFCC FFT tile: 400 complex = 3200 bytes
 constexpr int kShareBytes = 52 * 33 * 4;         // DCT-share transpose tile (the largest MFCC use of a warp's buffer)
 // top_db candidates of one warp live behind the transpose tile: 198 entries of (frame << 7 | filter, dB)

@@ -10,7 +10,7 @@ def need_gpu():
     return torch.device("cuda:0")
 
 
-def close(a, b, rel=1e-3, floor=1e-5, what=""):
+def close(a, b, rel=1e-3, floor=1e-6, what=""):
     """Tolerance of SURVEY.md section 8(d): |a-b| <= rel*|b| + floor, identical NaN pattern."""
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)

@@ -1,7 +1,7 @@
 """GPU parity of the fused feature kernel (through the C ABI) against the golden vectors of the
 reference, the numpy oracle, and size-independent properties at the benchmark size.
 
-Tolerances: timbre / rhythm[0:2] / quality floats rel 1e-3 (abs floor 1e-5);
+Tolerances: timbre / rhythm[0:2] / quality floats rel 1e-3 (abs floor 1e-6; 2e-5 against the reference's fp32 LayerNorm golden rows);
 rhythm[2] and speech_rate exact; "pitch" |v| <= 1e-6 absolute (the reference value is rounding
 noise ~1e-9); intensity NaN for mono; NaN pattern of the LayerNorm row identical.
 """
@@ -119,7 +119,7 @@ def test_adversarial_vs_golden(ana, golden_features, name):
     _, det, _ = _detail(ana, x[None])
     d = det[0]
     ref = {k: g[f"adv_{name}_{k}"] for k in ("pitch", "timbre", "speech_rate", "rhythm", "quality4")}
-    rel, floor = (1e-3, 1e-5) if name not in ("noise_1e-4", "zeros") else (2e-3, 2e-4)
+    rel, floor = (1e-3, 1e-6) if name not in ("noise_1e-4", "zeros") else (2e-3, 2e-4)
     assert abs(d[8]) <= 1e-6
     close(d[10:23], ref["timbre"], rel, floor, what="timbre")
     close(d[24:26], ref["rhythm"][:2], rel, 1e-9 + floor * 0, what="rhythm")
