@@ -5,7 +5,7 @@
 # by git, shipped to the GPU box by gpurun).  Prints the fp32 kernel's spills so a variant that spills is seen at once.
 #   scripts/build_variant.sh base                      # the tree as it is
 #   scripts/build_variant.sh try1 -DMSA_VAR_SOMETHING
-#   SRC=msa_fusion_tc.cu scripts/build_variant.sh pdl -DMSA_VAR_PDL      # programmatic dependent launch between the fusion layers
+#   scripts/build_variant.sh k1g3 -DMSA_K1_GROUPS=3                     # three wave-statistics load groups in flight
 #   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o scripts/ab_check scripts/ab_check.cu -ldl
 #   gpurun --timeout 60 -- 'timeout 45 ./scripts/ab_check scripts/ab/libmsa_base.so scripts/ab/libmsa_try1.so > gpurun_out/ab.json'
 # (≈ 25 s of box time per call: no Python, no torch import.)

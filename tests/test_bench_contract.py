@@ -15,7 +15,7 @@ def _latest(pattern):
 
 
 def test_native_line_has_the_contract_keys():
-    d = _latest("r1_v*_bench.json")
+    d = _latest("r2_v*_bench.json")
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in d, k
@@ -30,12 +30,20 @@ def test_native_line_has_the_contract_keys():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"]
     assert d["gpu_launches"] > 0 and d["n_gpus"] == 1 and d["warmup"] >= 3
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # every BASELINE config rides in the one line (round 2)
+    h = d["hour_sharded"]
+    assert h["segments"] == 720 and h["scaling"] == "strong" and h["ms"] > 0 and abs(h["value"] - 3600.0 / (h["ms"] / 1e3)) < 1e-3 * h["value"]
+    f = d["fusion_only_65536"]
+    assert f["rows"] == 65536 and f["ms"] > 0 and 0 < f["frac"] < 1 and abs(f["issued_bf16_tflops"] - 3 * f["algorithmic_tflops"]) < 1e-6
+    assert d["stream_latency"]["p50_ms"] > 0 and d["reference_api_call"]["p50_ms"] > 0
+    assert 0 < r["fp32"]["frac"] < 1 and r["msa_version"] >= 200
+    assert r["traffic"] is None or r["traffic"] >= r["algorithmic_bytes_per_launch"]
 
 
 def test_reference_line_has_the_contract_keys():
-    d = _latest("r1_v*_bench_reference.json")
+    d = _latest("r2_v*_bench_reference.json")
     assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "audio-s/s"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
-    n = _latest("r1_v*_bench.json")
+    n = _latest("r2_v*_bench.json")
     assert d["metric"] == n["metric"] and d["unit"] == n["unit"] and d["higher_is_better"] == n["higher_is_better"]
