@@ -117,11 +117,10 @@ int msa_fusion_pack(const float* const* tensors_host, void* packed_dev, void* st
 int msa_fusion_forward(const float* face, const float* audio, const float* text, int B, const void* packed,
                        void* workspace, size_t workspace_bytes, float* logits7, int32_t* argmax, void* stream);
 
-/* Select the implementation behind msa_fusion_forward: 0 = default (tcgen05 tensor-core kernels; batches of
- * up to 8 rows, i.e. the streaming path's one row per chunk, run as fp32 matrix-vector kernels instead),
- * 1 = fp32 CUDA-core bring-up kernels kept as an on-device cross-check (tests only; also selectable
- * with MSA_FUSION_IMPL=simt), 2 = tcgen05 kernels for every batch size.  Same ABI, same results to fp32
- * rounding. */
+/* Batch-size dispatch of msa_fusion_forward: 0 = default (tcgen05 tensor-core kernels; batches of up to 8 rows, i.e. the
+ * streaming path's one row per chunk, run as fp32 matrix-vector kernels instead), 2 = tcgen05 kernels for every batch size
+ * (also MSA_FUSION_IMPL=tc in the environment).  Same ABI, same results to fp32 rounding.  (Value 1, round 1's fp32
+ * CUDA-core cross-check, is no longer part of the library: it lives in tests/xcheck as test infrastructure.) */
 int msa_fusion_set_impl(int impl);
 
 /* ---- speaker / timeline aggregation (src/processors/offline_processor.py:259-298) --------- */

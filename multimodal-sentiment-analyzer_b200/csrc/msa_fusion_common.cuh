@@ -99,7 +99,7 @@ struct Workspace {
   size_t h_hi[3], h_lo[3];                                                     // bf16 [Bp, 1024] per modality
   size_t cat_hi, cat_lo;                                                       // bf16 [Bp, 1536]
   size_t f1_hi, f1_lo;                                                         // bf16 [Bp, 1024]
-  size_t f32_a, f32_b;                                                         // fp32 [Bp, 1536] scratch (bring-up path)
+  size_t f32_a, f32_b;                                                         // fp32 [128, 3072] scratch of the matrix-vector path (batches <= 8)
   size_t total;
   int Bp;
 };
@@ -115,7 +115,7 @@ inline void workspace_layout(int B, Workspace& w) {
   for (int m = 0; m < 3; ++m) { w.h_hi[m] = take(Bp * kHidden * 2); w.h_lo[m] = take(Bp * kHidden * 2); }
   w.cat_hi = take(Bp * 1536 * 2); w.cat_lo = take(Bp * 1536 * 2);
   w.f1_hi = take(Bp * kHidden * 2); w.f1_lo = take(Bp * kHidden * 2);
-  w.f32_a = take(Bp * 1536 * 4); w.f32_b = take(Bp * 1536 * 4);
+  w.f32_a = take((size_t)128 * 3072 * 4); w.f32_b = take((size_t)128 * 3072 * 4);
   w.total = off;
 }
 
