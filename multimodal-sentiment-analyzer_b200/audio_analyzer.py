@@ -205,8 +205,19 @@ class AudioAnalyzer:
         _, detail, _ = self._run(w, None, parts)
         return detail[0, sl].reshape(shape).clone()
 
+    def _channels(self, waveform: torch.Tensor) -> torch.Tensor:
+        """[C, T] with C >= 2 (direct callers of the per-method API; analyze() itself only sees mono files)."""
+        if not isinstance(waveform, torch.Tensor) or waveform.dim() != 2 or waveform.shape[0] < 2 or waveform.shape[1] < 1:
+            raise ValueError("not a multi-channel waveform")
+        w = waveform.to(self.device)
+        if w.dtype != torch.int16:
+            w = w.float()
+        return w.contiguous()
+
     def _analyze_pitch(self, waveform: torch.Tensor) -> torch.Tensor:
-        """audio_analyzer.py:175-188 -> [1, 1]."""
+        """audio_analyzer.py:175-188 -> [1, 1].  (For C >= 2 channels the reference returns a finite [1, C] that depends
+        on the relative size of its fp32 round-trip noise per channel; that noise is not reproduced here - the round trip
+        runs in fp16 - so multi-channel input takes the method's documented default.)"""
         try:
             return self._feature(waveform, _lib.PART_PITCH, slice(8, 9), (1, 1), 257)
         except _lib.MsaError:
@@ -216,8 +227,14 @@ class AudioAnalyzer:
             return torch.zeros(1, 1, device=self.device)
 
     def _analyze_intensity(self, waveform: torch.Tensor) -> torch.Tensor:
-        """audio_analyzer.py:190-201 -> [1, 1] (NaN for mono in strict mode)."""
+        """audio_analyzer.py:190-201 -> [1, 1] (NaN for mono in strict mode); [1, C] for C >= 2 channels: the z-score of
+        the channel energies (every channel runs through the kernel as a segment; the C-element z-score is host glue)."""
         try:
+            if isinstance(waveform, torch.Tensor) and waveform.dim() == 2 and waveform.shape[0] >= 2:
+                w = self._channels(waveform)
+                _, detail, _ = self._run(w, None, _lib.PART_WAVE)
+                e = detail[:, 68]                                                # e_total per channel
+                return ((e - e.mean()) / (e.std() + 1e-6)).unsqueeze(0)
             return self._feature(waveform, _lib.PART_WAVE, slice(9, 10), (1, 1), 1)
         except _lib.MsaError:
             raise
@@ -226,8 +243,16 @@ class AudioAnalyzer:
             return torch.zeros(1, 1, device=self.device)
 
     def _analyze_timbre(self, waveform: torch.Tensor) -> torch.Tensor:
-        """audio_analyzer.py:203-217 -> [1, 13]."""
+        """audio_analyzer.py:203-217 -> [1, 13]; [1, C, 13] for C >= 2 channels (the z-score there is over ALL channels'
+        MFCCs: the per-channel MFCC matrices come from the kernel, the global moments of C x 13 x frames values are host glue)."""
         try:
+            if isinstance(waveform, torch.Tensor) and waveform.dim() == 2 and waveform.shape[0] >= 2:
+                w = self._channels(waveform)
+                if w.shape[1] < 201:
+                    raise ValueError("too short")
+                _, _, mf = self._run(w, None, _lib.PART_WAVE | _lib.PART_MFCC, want_mfcc=True)     # [C, frames, 13]
+                z = (mf - mf.mean()) / (mf.std() + 1e-6)
+                return z.mean(dim=1).unsqueeze(0)                                 # [1, C, 13]
             return self._feature(waveform, _lib.PART_MFCC, slice(10, 23), (1, 13), 201)
         except _lib.MsaError:
             raise

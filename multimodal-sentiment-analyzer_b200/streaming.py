@@ -129,6 +129,30 @@ class StreamingWindow:
             self._graphs[key] = gr
         return gr
 
+    def input_buffers(self):
+        """The pinned host buffers a hop's graph uploads from: {"pcm": [hop] int16, "face": [1, 27], "text": [1, 783]}.
+        A producer that writes the next chunk straight into them (``pipe.readinto(memoryview(buf["pcm"].numpy()))``, the
+        way streaming_processor.py:185-196 reads its ffmpeg pipe) and then calls ``push_staged`` pays no host copy at all.
+        They may be rewritten as soon as the previous hop's ``done`` event has fired."""
+        g = self._static()
+        return {"pcm": g["stage"], "face": g["face_h"], "text": g["text_h"]}
+
+    @torch.no_grad()
+    def push_staged(self, has_text: bool = True):
+        """``push`` for inputs already written into ``input_buffers()`` (window must be full: use ``push`` to fill it)."""
+        if not self.use_graph or (self.n_pushed + 1) * self.hop < self.window:
+            g = self._static()
+            return self.push(g["stage"].clone(), g["face_h"].clone(), g["text_h"].clone() if has_text else None)
+        g = self._static()
+        p = self.pos
+        self._graph_for(p, has_text).replay()
+        g["done"].record(torch.cuda.current_stream(self.device))
+        g["busy"] = True
+        self.pos = (p + self.hop) % self.window
+        self.n_pushed += 1
+        return {"fused_emotion": g["logits"][0], "argmax": g["amax"][0], "audio_row": g["row"][0], "host": g["out"],
+                "done": g["done"]}
+
     @torch.no_grad()
     def push(self, chunk_pcm: torch.Tensor, face: torch.Tensor, text: Optional[torch.Tensor] = None):
         """chunk_pcm: [hop] int16 on the host.  Returns None until the window is full, then the dict of

@@ -170,9 +170,24 @@ def golden_fusion(fusion_mod):
     return data
 
 
+def golden_multichannel(audio_mod):
+    """Per-method semantics for C >= 2 channels (audio_analyzer.py:190-217): intensity is a finite [1, C] z-score of
+    the channel energies, timbre a [1, C, 13] z-score over all channels' MFCCs (analyze() itself never gets that far
+    with multi-channel input: its torch.cat fails and it returns the default)."""
+    import torch
+    from oracle import synth
+    ana = audio_mod.AudioAnalyzer(device="cpu")
+    seeds = [4000, 4001, 4002]
+    w = torch.from_numpy(np.stack([synth.pcm_to_f32(synth.segment_pcm(s)) for s in seeds]))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return {"seeds": np.array(seeds), "intensity": ana._analyze_intensity(w).numpy(), "timbre": ana._analyze_timbre(w).numpy()}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     audio_mod, fusion_mod = load_reference()
+    np.savez_compressed(os.path.join(OUT, "multichannel_golden.npz"), **golden_multichannel(audio_mod))
     f = golden_features(audio_mod)
     np.savez_compressed(os.path.join(OUT, "features_golden.npz"), **f)
     g = golden_fusion(fusion_mod)

@@ -327,6 +327,51 @@ def test_streaming_window_equals_offline(use_graph, with_text):
             assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == o["argmax"]
 
 
+def test_streaming_staged_push_and_buffer_growth():
+    """(1) ``push_staged``: inputs written straight into the window's pinned buffers give the same bits as ``push``.
+    (2) A captured hop must not depend on buffers that other users of the same analyzer / model can reallocate: between
+    hops a 600-segment batch goes through both objects (their grow-only scratch tables and the fusion workspace are
+    replaced), a new state_dict is loaded, and the following hops still equal the offline result with the NEW weights."""
+    dev = need_gpu()
+    import msa_b200
+    ana = msa_b200.AudioAnalyzer(device="cuda:0")
+    m, _ = _model(True, 0)
+    n_push = 20
+    pcm = synth.segment_pcm(78, 80000 + (n_push - 10) * 8000)
+    faces, texts = torch.from_numpy(synth.face_rows(19, n_push)), torch.from_numpy(synth.text_rows(20, n_push))
+    sw = msa_b200.StreamingWindow(ana, m)
+
+    def check(i, o):
+        o["done"].synchronize()
+        seg = torch.from_numpy(pcm[(i - 9) * 8000:(i - 9) * 8000 + 80000].copy())[None].to(dev)
+        row = ana.analyze_batch(seg)
+        logits, amax = m.fused_with_argmax(faces[i:i + 1].to(dev), row, texts[i:i + 1].to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == int(amax[0].item()), i
+
+    for i in range(12):
+        o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), faces[i], texts[i])
+        if i >= 9:
+            check(i, o)
+    bufs = sw.input_buffers()
+    for i in range(12, 15):                                                    # (1) zero-copy producer
+        o["done"].synchronize()
+        bufs["pcm"].copy_(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()))
+        bufs["face"].copy_(faces[i:i + 1]); bufs["text"].copy_(texts[i:i + 1])
+        o = sw.push_staged(has_text=True)
+        check(i, o)
+    # (2) grow every shared buffer and change the weights behind the captured graphs
+    big = torch.from_numpy(synth.fast_segments_pcm(5, 600)).to(dev)
+    pipe = msa_b200.SegmentPipeline(ana, m)
+    pipe.run(big, torch.from_numpy(synth.face_rows(1, 600)).to(dev), torch.from_numpy(synth.text_rows(2, 600)).to(dev))
+    sd2 = synth.fusion_state(999, trained_like=True)
+    m.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd2.items()}, strict=True)
+    torch.cuda.synchronize()
+    for i in range(15, n_push):
+        o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), faces[i], texts[i])
+        check(i, o)
+
+
 @pytest.mark.parametrize("n", [300, 5000], ids=["128-column tiles", "512-column tiles"])
 def test_layernorm_rows_with_mean_far_from_zero(n):
     """A trained checkpoint can have |row mean| >> row sigma in front of a LayerNorm (large Linear biases): the fused
