@@ -147,6 +147,8 @@ class SegmentPipeline:
         while the previous call's last kernels are still running and the copy engine never idles between calls."""
         n, T = pcm_host.shape
         dev = self.device
+        if n == 0:                                                # an empty batch has nothing to upload or compute
+            return torch.empty(0, ROW_WORDS, device=dev, dtype=torch.float32)
         cur = torch.cuda.current_stream(dev)
         st = self._host_state(chunk, T, text_host is not None, n)
         copy_s = st["copy_stream"]
