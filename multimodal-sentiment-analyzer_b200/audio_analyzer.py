@@ -243,16 +243,10 @@ class AudioAnalyzer:
             return torch.zeros(1, 1, device=self.device)
 
     def _analyze_timbre(self, waveform: torch.Tensor) -> torch.Tensor:
-        """audio_analyzer.py:203-217 -> [1, 13]; [1, C, 13] for C >= 2 channels (the z-score there is over ALL channels'
-        MFCCs: the per-channel MFCC matrices come from the kernel, the global moments of C x 13 x frames values are host glue)."""
+        """audio_analyzer.py:203-217 -> [1, 13].  (For C >= 2 channels the reference returns [1, C, 13] whose top_db clamp
+        uses the maximum over ALL channels - torchaudio packs the channels of a 3-D input into one clamp group - while
+        the kernel clamps every segment against its own maximum; multi-channel input takes the documented default.)"""
         try:
-            if isinstance(waveform, torch.Tensor) and waveform.dim() == 2 and waveform.shape[0] >= 2:
-                w = self._channels(waveform)
-                if w.shape[1] < 201:
-                    raise ValueError("too short")
-                _, _, mf = self._run(w, None, _lib.PART_WAVE | _lib.PART_MFCC, want_mfcc=True)     # [C, frames, 13]
-                z = (mf - mf.mean()) / (mf.std() + 1e-6)
-                return z.mean(dim=1).unsqueeze(0)                                 # [1, C, 13]
             return self._feature(waveform, _lib.PART_MFCC, slice(10, 23), (1, 13), 201)
         except _lib.MsaError:
             raise
