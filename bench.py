@@ -275,18 +275,20 @@ def run_native(args):
     launches = {"n": 0}
     pending = {"g": None}
 
-    pipe = msa_b200.SegmentPipeline(ana, model)
-
     def step_resident():
-        # the public batched call: feature kernel, the fusion forward (its audio-independent half on a second stream
-        # underneath the feature kernel's last wave), result-row packing
-        rows = pipe.run(wav_dev, face_dev, text_dev, first_id=rank * S)
-        launches["n"] += pipe.last_launches
+        row = ana.analyze_batch(wav_dev)
+        launches["n"] += lib.msa_last_launch_count()
+        logits, amax = model.fused_with_argmax(face_dev, row, text_dev)
+        launches["n"] += lib.msa_last_launch_count()
+        rows = pack_rows(row, logits, amax, rank * S)
+        launches["n"] += lib.msa_last_launch_count()
         # the one collective of the path runs behind this step's kernels on NCCL's stream and overlaps the next step; the
         # gather of the step before is waited for here (stream-level), so every step's table is complete inside the timed region
         pend = gather_rows_async(rows, S * world, world, rank)
         prev, pending["g"] = pending["g"], pend
         return prev.wait() if prev is not None else None
+
+    pipe = msa_b200.SegmentPipeline(ana, model)
 
     def step_e2e():
         # public host-buffer API: chunked upload on a copy stream overlapped with the kernels, one D2H of the rows

@@ -117,14 +117,6 @@ int msa_fusion_pack(const float* const* tensors_host, void* packed_dev, void* st
 int msa_fusion_forward(const float* face, const float* audio, const float* text, int B, const void* packed,
                        void* workspace, size_t workspace_bytes, float* logits7, int32_t* argmax, void* stream);
 
-/* The same forward in two calls, so that the part that does not need the audio rows can run on ANOTHER stream underneath the
- * feature kernel that produces them (the per-modality branches of fusion_model.py:296-305, 386-395 are independent until
- * the concatenation :397): which = 1: LayerNorm + projection + processor of face (and text when given); which = 2: the same
- * for audio, then the fusion layers, logits and arg-max.  Same buffers in both calls; part 2 must be ordered behind part 1
- * (event / stream wait).  The results are bit-identical to msa_fusion_forward. */
-int msa_fusion_forward_part(const float* face, const float* audio, const float* text, int B, const void* packed,
-                            void* workspace, size_t workspace_bytes, float* logits7, int32_t* argmax, int which, void* stream);
-
 /* Batch-size dispatch of msa_fusion_forward: 0 = default (tcgen05 tensor-core kernels; batches of up to 8 rows, i.e. the
  * streaming path's one row per chunk, run as fp32 matrix-vector kernels instead), 2 = tcgen05 kernels for every batch size
  * (also MSA_FUSION_IMPL=tc in the environment).  Same ABI, same results to fp32 rounding.  (Value 1, round 1's fp32

@@ -32,7 +32,6 @@ _SIGNATURES = {
     "msa_fusion_tensor_numel": (c_size_t, [c_int]),
     "msa_fusion_pack": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p]),
     "msa_fusion_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
-    "msa_fusion_forward_part": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
     "msa_fusion_set_impl": (c_int, [c_int]),
     "msa_resample_out_len": (c_int, [c_int, c_int, c_int]),
     "msa_resample_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

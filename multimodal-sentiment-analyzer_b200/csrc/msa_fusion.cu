@@ -56,7 +56,7 @@ int fusion_pack(const float* const* tensors_host, void* packed_dev, cudaStream_t
 
 int fusion_forward_tc(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
                       const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
-                      cudaStream_t s, int which);   // msa_fusion_tc.cu
+                      cudaStream_t s);   // msa_fusion_tc.cu
 int fusion_forward_rows(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
                         const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
                         cudaStream_t s);   // msa_fusion_rows.cu
@@ -119,28 +119,5 @@ extern "C" int msa_fusion_forward(const float* face, const float* audio, const f
     return fusion_forward_rows(face, audio, text, B, static_cast<const unsigned char*>(packed), h,
                                static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream);
   return fusion_forward_tc(face, audio, text, B, static_cast<const unsigned char*>(packed), h,
-                           static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream, 3);
-}
-
-extern "C" int msa_fusion_forward_part(const float* face, const float* audio, const float* text, int B, const void* packed,
-                                       void* workspace, size_t workspace_bytes, float* logits7, int32_t* argmax, int which,
-                                       void* stream) {
-  using namespace msa;
-  reset_launches();
-  if (which != 1 && which != 2) return MSA_ERR_BAD_ARGUMENT;
-  if (!face || !packed || !workspace || B < 0) return MSA_ERR_BAD_ARGUMENT;
-  if (which == 2 && (!audio || !logits7)) return MSA_ERR_BAD_ARGUMENT;
-  if (B == 0) return MSA_OK;
-  Workspace wl;
-  workspace_layout(B, wl);
-  if (workspace_bytes < wl.total) return MSA_ERR_WORKSPACE;
-  const PackedHeader& h = host_header();
-  if (fusion_impl() == 0 && B <= kFusionRowsMaxBatch) {
-    // a handful of rows: the matrix-vector kernels have no separable half; everything runs in part 2
-    if (which == 1) return MSA_OK;
-    return fusion_forward_rows(face, audio, text, B, static_cast<const unsigned char*>(packed), h,
-                               static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream);
-  }
-  return fusion_forward_tc(face, audio, text, B, static_cast<const unsigned char*>(packed), h,
-                           static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream, which);
+                           static_cast<unsigned char*>(workspace), wl, logits7, argmax, (cudaStream_t)stream);
 }

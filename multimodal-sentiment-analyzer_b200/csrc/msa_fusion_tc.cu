@@ -562,44 +562,31 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
   return MSA_OK;
 }
 
-// which: bit 0 = the branches that do not depend on the audio row (face, text: LayerNorm + projection + processor),
-//        bit 1 = the audio branch and the two fusion layers.  3 = the whole forward (all branches share their launches).
-// Split in two calls, the first can run on a second stream underneath the feature kernel that produces the audio rows.
 int fusion_forward_tc(const float* face, const float* audio, const float* text, int B, const unsigned char* packed,
                       const PackedHeader& h, unsigned char* ws, const Workspace& wl, float* logits7, int32_t* argmax,
-                      cudaStream_t s, int which) {
+                      cudaStream_t s) {
   const bool three = text != nullptr;
   const int Bp = wl.Bp;
   auto f32 = [&](int t) { return reinterpret_cast<const float*>(packed + h.f32_off[t]); };
   auto bf = [&](size_t off) { return reinterpret_cast<__nv_bfloat16*>(ws + off); };
 
-  // modalities handled by this call: 0 face, 1 audio, 2 text
-  int mods[3], nm = 0;
-  if (which & 1) { mods[nm++] = 0; if (three) mods[nm++] = 2; }
-  if (which & 2) mods[nm++] = 1;
-  const float* xin[3] = {face, audio, text};
-  const int nw[3] = {T_FACE_NORM_W, T_AUDIO_NORM_W, T_TEXT_NORM_W}, nb[3] = {T_FACE_NORM_B, T_AUDIO_NORM_B, T_TEXT_NORM_B};
-  const int dims[3] = {kFaceDim, kAudioDim, kTextDim};
-  const size_t xin_hi[3] = {wl.x_face_hi, wl.x_audio_hi, wl.x_text_hi}, xin_lo[3] = {wl.x_face_lo, wl.x_audio_lo, wl.x_text_lo};
-  const int xk[3] = {kFaceK, kAudioK, kTextK};
-  // column block of a modality in the concatenated activations: [face | audio | text]
-  const int cat_col[3] = {0, kHalf, 2 * kHalf};
-
   PrepArgs pa{};
-  for (int i = 0; i < nm; ++i) {
-    const int m = mods[i];
-    pa.x[i] = xin[m];
-    pa.gamma[i] = f32(nw[m]); pa.beta[i] = f32(nb[m]);
-    pa.hi[i] = bf(xin_hi[m]); pa.lo[i] = bf(xin_lo[m]);
-    pa.d[i] = dims[m]; pa.kpad[i] = xk[m];
-  }
-  pa.B = B; pa.Bp = Bp; pa.nmod = nm;
-  if (nm > 0) {
-    tc_input_prep_kernel<<<dim3((Bp + 7) / 8, nm), 256, 0, s>>>(pa);
-    note_launches(1);
-  }
+  pa.x[0] = face; pa.x[1] = audio; pa.x[2] = text;
+  pa.gamma[0] = f32(T_FACE_NORM_W); pa.beta[0] = f32(T_FACE_NORM_B);
+  pa.gamma[1] = f32(T_AUDIO_NORM_W); pa.beta[1] = f32(T_AUDIO_NORM_B);
+  pa.gamma[2] = f32(T_TEXT_NORM_W); pa.beta[2] = f32(T_TEXT_NORM_B);
+  pa.hi[0] = bf(wl.x_face_hi); pa.lo[0] = bf(wl.x_face_lo);
+  pa.hi[1] = bf(wl.x_audio_hi); pa.lo[1] = bf(wl.x_audio_lo);
+  pa.hi[2] = bf(wl.x_text_hi); pa.lo[2] = bf(wl.x_text_lo);
+  pa.d[0] = kFaceDim; pa.d[1] = kAudioDim; pa.d[2] = kTextDim;
+  pa.kpad[0] = kFaceK; pa.kpad[1] = kAudioK; pa.kpad[2] = kTextK;
+  pa.B = B; pa.Bp = Bp; pa.nmod = three ? 3 : 2;
+  tc_input_prep_kernel<<<dim3((Bp + 7) / 8, pa.nmod), 256, 0, s>>>(pa);
+  note_launches(1);
 
   const int cat_w = three ? 1536 : 1024;
+  const size_t xin_hi[3] = {wl.x_face_hi, wl.x_audio_hi, wl.x_text_hi}, xin_lo[3] = {wl.x_face_lo, wl.x_audio_lo, wl.x_text_lo};
+  const int xk[3] = {kFaceK, kAudioK, kTextK};
   const int proj_g[3] = {G_FACE_PROJ, G_AUDIO_PROJ, G_TEXT_PROJ}, proj_b[3] = {T_FACE_PROJ_B, T_AUDIO_PROJ_B, T_TEXT_PROJ_B};
   const int l0w[3] = {T_FACE_P0_W, T_AUDIO_P0_W, T_TEXT_P0_W}, l0b[3] = {T_FACE_P0_B, T_AUDIO_P0_B, T_TEXT_P0_B};
   const int p3_g[3] = {G_FACE_P3, G_AUDIO_P3, G_TEXT_P3}, p3_b[3] = {T_FACE_P3_B, T_AUDIO_P3_B, T_TEXT_P3_B};
@@ -607,22 +594,17 @@ int fusion_forward_tc(const float* face, const float* audio, const float* text, 
   int rc;
   // the modality branches are independent: all projections in one launch, all processors in the next
   LayerLaunch proj[3], proc[3];
-  for (int i = 0; i < nm; ++i) {
-    const int m = mods[i];
-    proj[i] = LayerLaunch{bf(xin_hi[m]), bf(xin_lo[m]), xk[m], proj_g[m], proj_b[m], l0w[m], l0b[m], bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, 0, false};
-    proc[i] = LayerLaunch{bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, p3_g[m], p3_b[m], l4w[m], l4b[m], bf(wl.cat_hi), bf(wl.cat_lo), cat_w, cat_col[m], false};
+  for (int m = 0; m < pa.nmod; ++m) {
+    proj[m] = LayerLaunch{bf(xin_hi[m]), bf(xin_lo[m]), xk[m], proj_g[m], proj_b[m], l0w[m], l0b[m], bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, 0, false};
+    proc[m] = LayerLaunch{bf(wl.h_hi[m]), bf(wl.h_lo[m]), kHidden, p3_g[m], p3_b[m], l4w[m], l4b[m], bf(wl.cat_hi), bf(wl.cat_lo), cat_w, m * kHalf, false};
   }
-  if (nm > 0) {
-    if ((rc = launch_layers(proj, nm, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
-    if ((rc = launch_layers(proc, nm, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
-  }
-  if (which & 2) {
-    LayerLaunch f0{bf(wl.cat_hi), bf(wl.cat_lo), cat_w, three ? G_FUS0 : G_FUS2, three ? T_FUS0_B : T_FUS2_B, T_FUS1_W, T_FUS1_B,
-                   bf(wl.f1_hi), bf(wl.f1_lo), kHidden, 0, false};
-    if ((rc = launch_layers(&f0, 1, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
-    LayerLaunch f4{bf(wl.f1_hi), bf(wl.f1_lo), kHidden, G_FUS4, T_FUS4_B, T_FUS5_W, T_FUS5_B, nullptr, nullptr, 0, 0, true};
-    if ((rc = launch_layers(&f4, 1, B, Bp, packed, h, logits7, argmax, s))) return rc;
-  }
+  if ((rc = launch_layers(proj, pa.nmod, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  if ((rc = launch_layers(proc, pa.nmod, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  LayerLaunch f0{bf(wl.cat_hi), bf(wl.cat_lo), cat_w, three ? G_FUS0 : G_FUS2, three ? T_FUS0_B : T_FUS2_B, T_FUS1_W, T_FUS1_B,
+                 bf(wl.f1_hi), bf(wl.f1_lo), kHidden, 0, false};
+  if ((rc = launch_layers(&f0, 1, B, Bp, packed, h, nullptr, nullptr, s))) return rc;
+  LayerLaunch f4{bf(wl.f1_hi), bf(wl.f1_lo), kHidden, G_FUS4, T_FUS4_B, T_FUS5_W, T_FUS5_B, nullptr, nullptr, 0, 0, true};
+  if ((rc = launch_layers(&f4, 1, B, Bp, packed, h, logits7, argmax, s))) return rc;
   return (int)cudaGetLastError();
 }
 

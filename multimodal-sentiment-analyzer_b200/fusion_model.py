@@ -160,23 +160,6 @@ class AdvancedFusionModel(nn.Module):
                                            ws.numel(), _lib.ptr(logits_out), _lib.ptr(argmax_out), _lib.current_stream_ptr(dev))
         _lib.check(rc, "msa_fusion_forward")
 
-    def forward_part(self, which: int, face: torch.Tensor, audio: Optional[torch.Tensor], text: Optional[torch.Tensor],
-                     logits_out: Optional[torch.Tensor], argmax_out: Optional[torch.Tensor]) -> None:
-        """One half of the forward on the CURRENT stream (``msa_fusion_forward_part``): which = 1 runs the branches that
-        do not need the audio rows (face, text), which = 2 the audio branch, the fusion layers, logits and arg-max.
-        Contiguous fp32 device tensors; ``prepare(B)`` first; the caller orders part 2 behind part 1.  ``SegmentPipeline.run``
-        uses it to run part 1 on a second stream underneath the feature kernel."""
-        B = face.shape[0]
-        need = _lib.lib().msa_fusion_workspace_bytes(B)
-        if self._packed is None or self._workspace is None or self._workspace.numel() < need:
-            raise _lib.MsaError("forward_part: call prepare(B) first (weights packed, workspace sized)")
-        ws = self._workspace
-        with _lib.on_device(self.device):
-            rc = _lib.lib().msa_fusion_forward_part(_lib.ptr(face), _lib.ptr(audio), _lib.ptr(text), B, _lib.ptr(self._packed), _lib.ptr(ws),
-                                                    ws.numel(), _lib.ptr(logits_out), _lib.ptr(argmax_out), int(which),
-                                                    _lib.current_stream_ptr(self.device))
-        _lib.check(rc, "msa_fusion_forward_part")
-
     def prepare(self, B: int) -> None:
         """Pack the weights and size the workspace for batches of up to B rows (allocation happens here, never in
         ``forward_into``)."""

@@ -123,60 +123,15 @@ class SegmentPipeline:
         self.analyzer = analyzer
         self.fusion = fusion
         self.device = analyzer.device
-        self.overlap_fusion = True     # run the audio-independent half of the fusion on a second stream (see run)
-        self.last_launches = 0
 
     @torch.no_grad()
     def run(self, waves: torch.Tensor, face: torch.Tensor, text: Optional[torch.Tensor] = None,
             emotion_probs: Optional[torch.Tensor] = None, first_id: int = 0) -> torch.Tensor:
         """waves [n, T] (fp32 or int16 PCM), face [n, 27], text [n, 783] or None (the live streaming
         path has no text, streaming_processor.py:420-424) -> result table [n, 40]."""
-        n = waves.shape[0]
-        if n <= 8 or not self.overlap_fusion:
-            count = _lib.lib().msa_last_launch_count
-            audio_row = self.analyzer.analyze_batch(waves, emotion_probs)
-            launches = count()
-            logits, amax = self.fusion.fused_with_argmax(face, audio_row, text)
-            launches += count()
-            rows = pack_rows(audio_row, logits, amax, first_id)
-            self.last_launches = launches + count()
-            return rows
-        # The face and text branches of the fusion model (LayerNorm, projection, processor: 3 of its 5 launches) do not
-        # need the audio rows: they go to a second stream BEHIND the feature kernel in launch order, so their CTAs fill
-        # the SMs the feature kernel's last, partly empty wave leaves idle; the audio branch and the fusion layers
-        # follow on the main stream.  Same kernels, same buffers: bit-identical to the one-call forward.
-        dev = self.device
-        fus = self.fusion
-        prep = lambda t: t.detach().to(dev, torch.float32).reshape(n, -1).contiguous()
-        f = prep(face)
-        t = prep(text) if text is not None else None
-        fus.prepare(n)
-        logits = torch.empty(n, 7, device=dev, dtype=torch.float32)
-        amax = torch.empty(n, device=dev, dtype=torch.int32)
-        cur = torch.cuda.current_stream(dev)
-        side = self._side_stream()
-        ready = torch.cuda.Event()
-        ready.record(cur)                                            # inputs and the workspace's previous user are done
-        count = _lib.lib().msa_last_launch_count
-        audio_row = self.analyzer.analyze_batch(waves, emotion_probs)   # the feature kernel is launched FIRST
-        launches = count()
-        with torch.cuda.stream(side):
-            side.wait_event(ready)
-            fus.forward_part(1, f, None, t, None, None)
-            launches += count()
-            done1 = torch.cuda.Event()
-            done1.record(side)
-        cur.wait_event(done1)
-        fus.forward_part(2, f, audio_row, t, logits, amax)
-        launches += count()
-        rows = pack_rows(audio_row, logits, amax, first_id)
-        self.last_launches = launches + count()                      # kernels this call launched (bench accounting)
-        return rows
-
-    def _side_stream(self):
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(self.device)
-        return self._side
+        audio_row = self.analyzer.analyze_batch(waves, emotion_probs)
+        logits, amax = self.fusion.fused_with_argmax(face, audio_row, text)
+        return pack_rows(audio_row, logits, amax, first_id)
 
     @torch.no_grad()
     def run_host(self, pcm_host: torch.Tensor, face_host: torch.Tensor, text_host: Optional[torch.Tensor],

@@ -327,29 +327,6 @@ def test_streaming_window_equals_offline(use_graph, with_text):
             assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == o["argmax"]
 
 
-@pytest.mark.parametrize("n,with_text", [(300, True), (1024, True), (77, False), (5000, True)])
-def test_overlapped_fusion_halves_equal_the_single_call(n, with_text):
-    """SegmentPipeline.run launches the face / text branches of the fusion model on a second stream underneath the feature
-    kernel (msa_fusion_forward_part, which = 1) and the audio branch + fusion layers behind it (which = 2): same kernels
-    and buffers, so the result table is bit-identical to the one-call forward - also when calls follow each other
-    back to back (the second call's part 1 must wait for the first call's part 2: shared workspace)."""
-    dev = need_gpu()
-    import msa_b200
-    ana = msa_b200.AudioAnalyzer(device="cuda:0")
-    m, _ = _model(True, 0)
-    pcm = torch.from_numpy(synth.fast_segments_pcm(21, n)).to(dev)
-    (f, a, t), (fd, ad, td) = _inputs(n, dev)
-    pipe = msa_b200.SegmentPipeline(ana, m)
-    pipe.overlap_fusion = False
-    ref = pipe.run(pcm, fd, td if with_text else None, first_id=7).clone()
-    pipe.overlap_fusion = True
-    outs = [pipe.run(pcm, fd, td if with_text else None, first_id=7) for _ in range(3)]   # back to back, no sync in between
-    torch.cuda.synchronize()
-    for o in outs:
-        assert torch.equal(o.view(torch.int32), ref.view(torch.int32))
-    assert pipe.last_launches == 1 + 3 + 5 + 1                                            # features, part 1, part 2, packing
-
-
 def test_streaming_staged_push_and_buffer_growth():
     """(1) ``push_staged``: inputs written straight into the window's pinned buffers give the same bits as ``push``.
     (2) A captured hop must not depend on buffers that other users of the same analyzer / model can reallocate: between
