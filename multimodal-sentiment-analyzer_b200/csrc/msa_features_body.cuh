@@ -12,21 +12,23 @@
 //   AudioFeatureNormalizer.normalize (src/utils/normalization.py:26-44) -> LayerNorm(31)
 //   audio row for fusion (src/processors/streaming_processor.py:250-268, 295-298)
 //
-// Work unit = one WARP x one QUAD of four consecutive STFT frames, i.e. two complex FFTs with
-// two real frames packed in each (re, im).  Every FFT pass runs in registers (msa_fft.cuh):
-//   pass A   lane n2 : 16 strided samples x window -> radix-16 -> inter-pass twiddle -> smem [k1][n2]
-//   pass B   lane k1 : one row -> radix-32 (radix-25 for n_fft 400); lanes 0-15 serve the first
-//            FFT of the quad, lanes 16-31 the second, so every lane is busy
-// so a transform crosses shared memory once per direction.  The waveform is read straight from
-// global memory (each 128-byte line reaches the SM from HBM once and is re-read from L1 by the
-// overlapping frames); nothing but constant tables and small per-warp tiles lives in shared memory.
+// Work unit = one WARP x one QUAD of four consecutive frames.
 //
-//   "pitch"  B is followed at once, in the same registers, by the inverse radix-32 (the vocoder at
-//            rate 1.0 returns its input), then the inverse pass A, the synthesis window and the
-//            overlap-add of the quad's 4 frames in registers.  Every warp owns a contiguous run of
-//            quads and carries the 3 hop-blocks that overlap the next quad in registers.
-//   MFCC     power of both packed frames from Z_k and Z_(N-k), sparse mel (each lane owns 4 filters),
-//            dB, and the lane's share of the DCT; a 52 x 32 shared-memory transpose sums the shares.
+//   "pitch"  (n_fft 512, hop 128; msa_pitch_tc.cuh)  STFT -> vocoder at rate 1.0 (identity) -> ISTFT as four chained
+//            mma.sync stages per pair of frames: 512 = 16 x 32, the DFT-16 / DFT-32 factors and their conjugates are
+//            constant fp16 A operands, the accumulator layout of one stage is the B layout of the next, the
+//            inter-stage twiddles are half2 FMAs, and the last stage's rows are rotated so that the overlap-add of
+//            consecutive frames stays in registers.  Every warp owns a contiguous run of quads, stages the waveform
+//            as fp16 into a swizzled 2048-sample ring of its own and reads the original samples back from it for
+//            |x - x^|.  The feature is the mean of a z-scored sequence, 0 up to 1e-6 whatever the residual, so fp16
+//            tensor-core arithmetic is free; the residual's moments still accumulate in fp32 / fp64.
+//   MFCC     (n_fft 400, hop 160; msa_fft.cuh)  two real frames packed per complex FFT, every pass in registers:
+//            pass A lane n2: 16 strided samples x window -> radix-16 -> twiddle -> smem [k1][n2];  pass B lane k1: one
+//            row -> radix-25.  The waveform is read straight from global memory (each 128-byte line reaches the SM
+//            from HBM once and is re-read from L1 by the overlapping frames).
+//            Power of both packed frames from Z_k and Z_(N-k), sparse mel (each lane owns 4 filters), dB, then the
+//            DCT 128 -> 13 of the quad's four frames as mma.sync with the dB values split into fp16 hi + lo words
+//            (three products, fp32 accumulate: error below 1e-6 of the coefficients).
 //            top_db needs the segment maximum, which is only known after the last frame: the DCT is
 //            linear, so the four EMPTY mel filters (max(-100, max-80) dB in every frame) enter as one
 //            constant vector afterwards, and the few live values that can fall below max-80 dB (known
