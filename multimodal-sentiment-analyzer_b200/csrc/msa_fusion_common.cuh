@@ -93,7 +93,9 @@ inline void packed_layout(PackedHeader& h) {
   h.total_bytes = off;
 }
 
-// Activation workspace for batch B (rows padded to a multiple of 128 = one MMA tile of rows).
+constexpr int kSmallBatchRows = 4096;                      // at or below: one CTA per 128 rows x 128 columns; above: CTA pairs per 256 rows x 512 columns
+
+// Activation workspace for batch B (rows padded to one MMA tile of rows: 128, or 256 where CTA pairs run).
 struct Workspace {
   size_t x_face_hi, x_face_lo, x_audio_hi, x_audio_lo, x_text_hi, x_text_lo;   // bf16 [Bp, Kpad] LayerNorm'd inputs
   size_t h_hi[3], h_lo[3];                                                     // bf16 [Bp, 1024] per modality
@@ -105,7 +107,8 @@ struct Workspace {
 };
 
 inline void workspace_layout(int B, Workspace& w) {
-  const size_t Bp = (size_t)((B + 127) / 128) * 128;
+  const size_t tile = B > kSmallBatchRows ? 256 : 128;
+  const size_t Bp = ((size_t)B + tile - 1) / tile * tile;
   w.Bp = (int)Bp;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 1024); return o; };
