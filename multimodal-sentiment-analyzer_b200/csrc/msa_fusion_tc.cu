@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "msa_api_internal.h"
@@ -136,6 +137,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float* v) {       // 64 consecutive columns: two loads, one wait
+  uint32_t r[64];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[32 * h + 0]), "=r"(r[32 * h + 1]), "=r"(r[32 * h + 2]), "=r"(r[32 * h + 3]), "=r"(r[32 * h + 4]), "=r"(r[32 * h + 5]),
+          "=r"(r[32 * h + 6]), "=r"(r[32 * h + 7]), "=r"(r[32 * h + 8]), "=r"(r[32 * h + 9]), "=r"(r[32 * h + 10]), "=r"(r[32 * h + 11]),
+          "=r"(r[32 * h + 12]), "=r"(r[32 * h + 13]), "=r"(r[32 * h + 14]), "=r"(r[32 * h + 15]), "=r"(r[32 * h + 16]), "=r"(r[32 * h + 17]),
+          "=r"(r[32 * h + 18]), "=r"(r[32 * h + 19]), "=r"(r[32 * h + 20]), "=r"(r[32 * h + 21]), "=r"(r[32 * h + 22]), "=r"(r[32 * h + 23]),
+          "=r"(r[32 * h + 24]), "=r"(r[32 * h + 25]), "=r"(r[32 * h + 26]), "=r"(r[32 * h + 27]), "=r"(r[32 * h + 28]), "=r"(r[32 * h + 29]),
+          "=r"(r[32 * h + 30]), "=r"(r[32 * h + 31])
+        : "r"(taddr + 32 * h));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // Up to three independent layers of the same shape class (the per-modality branches of fusion_model.py:44-86)
@@ -707,6 +728,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_pair_linear_ln_kernel(const 
   }
 }
 
+}  // namespace msa
+#include "msa_fusion_pair.cuh"
+namespace msa {
+
 // ------------------------------------------------------------------------------ input LayerNorm + split
 // One warp per row and modality: y = LN(x) * gamma + beta -> (hi, lo) bf16, K zero-padded; rows >= B zeroed.
 struct PrepArgs {
@@ -721,9 +746,49 @@ struct PrepArgs {
 
 constexpr int kPrepMaxK = 832;                                           // 783 padded to a multiple of 64
 
-__global__ void __launch_bounds__(256) tc_input_prep_kernel(const PrepArgs a) {
+// One row of one modality, NI = ceil(d / 32) column groups in registers (all loads of the row in flight at once)
+template <int NI>
+__device__ __forceinline__ void prep_row(const float* x, const float* gamma, const float* beta, int d, int kpad, int lane,
+                                         __nv_bfloat16* sh, __nv_bfloat16* sl) {
+  float v[NI];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = (c < d) ? x[c] : 0.0f;
+    sum += v[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)d;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const int c = lane + 32 * i;
+    const float dd = (c < d) ? v[i] - mean : 0.0f;
+    sq = fmaf(dd, dd, sq);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NI + 1; ++i) {                                     // kpad <= 32 (NI + 1)
+    const int c = lane + 32 * i;
+    if (c < kpad) {
+      float y = 0.0f;
+      if (c < d) y = (v[i < NI ? i : NI - 1] - mean) * rstd * gamma[c] + beta[c];
+      const __nv_bfloat16 h = __float2bfloat16_rn(y);
+      sh[c] = h;
+      sl[c] = __float2bfloat16_rn(y - __bfloat162float(h));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) tc_input_prep_kernel(const PrepArgs a) {
   // the warp's row is normalised with lane-strided columns (coalesced loads), staged as bf16 pairs in shared memory and
-  // written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at a quarter of the HBM rate
+  // written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at a quarter of the HBM rate.
+  // The 27- and 31-column rows of the face and audio branches take the one-group instance, not 25 predicated trips of
+  // the 783-column text rows (they were two thirds of this kernel's instructions: 240 us at 65,536 rows).
   __shared__ __align__(16) __nv_bfloat16 stage[8][2][kPrepMaxK];
   const int m = blockIdx.y;
   const int w = threadIdx.x >> 5;
@@ -737,38 +802,8 @@ __global__ void __launch_bounds__(256) tc_input_prep_kernel(const PrepArgs a) {
     return;
   }
   const float* x = a.x[m] + (size_t)row * d;
-  float v[25];                                                           // 783 <= 25 * 32
-  float sum = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 25; ++i) {
-    const int c = lane + 32 * i;
-    v[i] = (c < d) ? x[c] : 0.0f;
-    sum += v[i];
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / (float)d;
-  float sq = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 25; ++i) {
-    const int c = lane + 32 * i;
-    const float dd = (c < d) ? v[i] - mean : 0.0f;
-    sq = fmaf(dd, dd, sq);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq / (float)d + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < 26; ++i) {
-    const int c = lane + 32 * i;
-    if (c < kpad) {
-      float y = 0.0f;
-      if (c < d) y = (v[i < 25 ? i : 24] - mean) * rstd * a.gamma[m][c] + a.beta[m][c];
-      const __nv_bfloat16 h = __float2bfloat16_rn(y);
-      stage[w][0][c] = h;
-      stage[w][1][c] = __float2bfloat16_rn(y - __bfloat162float(h));
-    }
-  }
+  if (d <= 32) prep_row<1>(x, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);
+  else prep_row<25>(x, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);   // 783 <= 25 * 32
   __syncwarp();
   const uint4* sh = reinterpret_cast<const uint4*>(stage[w][0]);
   const uint4* sl = reinterpret_cast<const uint4*>(stage[w][1]);
@@ -791,18 +826,19 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] -> TMA map with box [box_rows, 64 cols], 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+// bf16 row-major [rows, cols] -> TMA map with box [box_rows, box_cols]: 64 columns with the 128-byte swizzle (operand
+// tiles), or 32 columns with the 64-byte swizzle (the persistent pair kernel's store tiles)
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = BLOCK_K) {
   if (!base) { std::memset(map, 0, sizeof(*map)); return MSA_OK; }    // the last layer stores no activations
   EncodeTiledFn enc = get_encode();
   if (!enc) return MSA_ERR_BAD_ARGUMENT;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {BLOCK_K, box_rows};
+  cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MSA_OK : 1000 + (int)r;
 }
 
@@ -862,6 +898,46 @@ static cudaError_t launch_pair_variant(const TcBatch& batch, int Bp, int N, int 
   return cudaLaunchKernelEx(&cfg, tc_pair_linear_ln_kernel<CLN, kFinal>, batch);
 }
 
+template <int CLN, bool kFinal>
+static cudaError_t launch_pair_persistent(const TcBatch& batch, int Bp, int N, int count, cudaStream_t s) {
+  auto kern = tc_pair_persistent_kernel<CLN, kFinal>;
+  constexpr int smem = pp_smem_bytes<kFinal>();
+  if (Bp % (2 * BLOCK_M) != 0 || N != 512 * CLN) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  PpSched sched{Bp / (2 * BLOCK_M), count};
+  const int total = sched.count * sched.tiles_per_branch;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(kPpThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = CLN;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  // clusters that fit the device at once (asked once per device and variant): the launch is exactly that many
+  static int fit[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (fit[dev] == 0) {
+    cfg.gridDim = dim3(2 * 148, CLN, 1);
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    if (e != cudaSuccess) return e;
+    if (n < 1) return cudaErrorLaunchOutOfResources;
+    fit[dev] = n;
+  }
+  const int G = total < fit[dev] ? total : fit[dev];
+  cfg.gridDim = dim3(2 * G, CLN, 1);
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kern, batch, sched);
+}
+
 // One launch for `count` (1..3) layers of the same output width (all 1024-wide or all 512-wide).
 static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const unsigned char* packed, const PackedHeader& h,
                          float* logits, int32_t* argmax, cudaStream_t s) {
@@ -879,8 +955,9 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     if ((rc = make_map(&batch.maps[i][1], L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
     if ((rc = make_map(&batch.maps[i][2], packed + h.hi_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
     if ((rc = make_map(&batch.maps[i][3], packed + h.lo_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
-    if ((rc = make_map(&batch.maps[i][4], L.out_hi, Bp, L.ld_out, 32))) return rc;
-    if ((rc = make_map(&batch.maps[i][5], L.out_lo, Bp, L.ld_out, 32))) return rc;
+    static const bool persist = !(getenv("MSA_PAIR_MODE") && getenv("MSA_PAIR_MODE")[0] == '0');
+    if ((rc = make_map(&batch.maps[i][4], L.out_hi, Bp, L.ld_out, 32, (!small && persist) ? 32 : BLOCK_K))) return rc;
+    if ((rc = make_map(&batch.maps[i][5], L.out_lo, Bp, L.ld_out, 32, (!small && persist) ? 32 : BLOCK_K))) return rc;
     TcEpilogue& ep = batch.ep[i];
     ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
     ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
@@ -898,14 +975,18 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     ep.argmax = argmax;
   }
   const bool fin = Ls[0].final_layer;
+  static const bool persist = !(getenv("MSA_PAIR_MODE") && getenv("MSA_PAIR_MODE")[0] == '0');
   batch.trace_slot = fin ? 3 : (N == 1024 ? (count > 1 ? 0 : 2) : 1);    // projections, processors, fusion.0, fusion.4
   cudaError_t e;
   if (N == 1024) {
     if (fin) return MSA_ERR_BAD_ARGUMENT;
-    e = small ? launch_variant<128, 8, false>(batch, Bp, N, count, s) : launch_pair_variant<2, false>(batch, Bp, N, count, s);
+    e = small ? launch_variant<128, 8, false>(batch, Bp, N, count, s)
+              : (persist ? launch_pair_persistent<2, false>(batch, Bp, N, count, s) : launch_pair_variant<2, false>(batch, Bp, N, count, s));
   } else if (N == 512) {
-    if (fin) e = small ? launch_variant<128, 4, true>(batch, Bp, N, count, s) : launch_pair_variant<1, true>(batch, Bp, N, count, s);
-    else e = small ? launch_variant<128, 4, false>(batch, Bp, N, count, s) : launch_pair_variant<1, false>(batch, Bp, N, count, s);
+    if (fin) e = small ? launch_variant<128, 4, true>(batch, Bp, N, count, s)
+                       : (persist ? launch_pair_persistent<1, true>(batch, Bp, N, count, s) : launch_pair_variant<1, true>(batch, Bp, N, count, s));
+    else e = small ? launch_variant<128, 4, false>(batch, Bp, N, count, s)
+                   : (persist ? launch_pair_persistent<1, false>(batch, Bp, N, count, s) : launch_pair_variant<1, false>(batch, Bp, N, count, s));
   } else {
     return MSA_ERR_BAD_ARGUMENT;
   }

@@ -78,6 +78,24 @@ int main(int argc, char** argv) {
       printf(", \"trace_cycles\": {");
       for (int sl = 0; sl < S; ++sl) {
         auto at = [&](int e, int c) { return t[((size_t)sl * E + e) * C + c]; };
+        if (getenv("MSA_PAIR_MODE") == nullptr || getenv("MSA_PAIR_MODE")[0] != '0') {
+          // persistent kernel: per-CTA SUMS over its tiles; event 7 carries the tile count in its upper bits
+          double a[8] = {0}; long long nc = 0, nlead = 0, tiles = 0;
+          for (int c = 0; c < C; ++c) {
+            const long long e7 = at(7, c);
+            if (e7 == 0) continue;
+            ++nc; tiles += e7 >> 40;
+            for (int e = 3; e < 7; ++e) a[e] += (double)at(e, c);
+            a[7] += (double)(e7 & ((1ll << 40) - 1));
+            if (at(2, c) != 0) { ++nlead; for (int e = 0; e < 3; ++e) a[e] += (double)at(e, c); }
+          }
+          if (!nc) continue;
+          const double tp = (double)tiles / nc;
+          printf("%s\"%s\": {\"ctas\": %lld, \"tiles_per_cta\": %.2f, \"per_tile\": {\"mma_wait_tmem\": %.0f, \"mma_wait_full\": %.0f, \"mma_issue\": %.0f, \"epi_wait_accum\": %.0f, \"epi_pass1\": %.0f, \"epi_tmem_ld\": %.0f, \"epi_pass2\": %.0f, \"epi_release\": %.0f}}",
+                 sl ? ", " : "", names[sl], nc, tp, nlead ? a[0] / nlead / tp : 0.0, nlead ? a[1] / nlead / tp : 0.0, nlead ? a[2] / nlead / tp : 0.0,
+                 a[3] / nc / tp, a[4] / nc / tp, a[5] / nc / tp, a[6] / nc / tp, a[7] / nc / tp);
+          continue;
+        }
         double d[8] = {0}; long long n = 0, nl = 0; double lead[2] = {0, 0};
         for (int c = 0; c < C; ++c) {
           if (at(0, c) == 0 || at(7, c) == 0) continue;
