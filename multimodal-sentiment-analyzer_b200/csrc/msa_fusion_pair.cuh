@@ -310,11 +310,15 @@ __global__ void __launch_bounds__(kPpThreads, 1) tc_pair_persistent_kernel(const
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         const int c0 = h * N_SUB + sub * 128;
+        uint32_t rv[32];
+        tmem_ld32_issue(trow + c0, rv);
 #pragma unroll 1
         for (int c = c0; c < c0 + 128; c += 32) {
           float v[32];
           PP_ACC(e_p2);
-          tmem_ld32(trow + c, v);
+          tmem_ld32_wait(rv);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(rv[i]);
           PP_ACC(e_ld);
           const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
           // ((v + bias - mean) * rstd) * gamma + beta, two columns per packed instruction
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) tc_pair_persistent_kernel(const
                 acc2[j] = __ffma2_rn(yb, make_float2(w4.z, w4.w), acc2[j]);
               }
             }
+            if (c + 32 < c0 + 128) tmem_ld32_issue(trow + c + 32, rv);
           } else {
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -352,6 +357,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) tc_pair_persistent_kernel(const
               lo[i / 2] = *reinterpret_cast<const uint32_t*>(&la);
               lo[i / 2 + 1] = *reinterpret_cast<const uint32_t*>(&lb);
             }
+            if (c + 32 < c0 + 128) tmem_ld32_issue(trow + c + 32, rv);   // in flight while this chunk is stored
             // through the warp's staging tile (64-byte rows, chunk ^ ((row >> 1) & 3): conflict-free both ways) to global
             // memory, hi then lo: four lanes cover one row's 64 bytes, eight rows per instruction
             const int ch = lane & 3;

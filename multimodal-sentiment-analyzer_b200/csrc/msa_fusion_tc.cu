@@ -7,15 +7,14 @@
 // so each product is issued as three bf16 MMAs with fp32 accumulation in tensor memory:
 //   X W^T ~= Xhi Whi^T + Xlo Whi^T + Xhi Wlo^T      (relative error ~2^-16)
 //
-// Kernel shape: one CTA owns 128 rows x NC output columns in tensor memory (thread <-> TMEM lane <-> row in the
-// epilogue), and the N / NC CTAs that share a row block form a cluster which exchanges the per-row LayerNorm
-// statistics (sum, sum of squares) - and, in the last layer, the partial 7 logits - through distributed shared
-// memory, always summed in rank order so every CTA sees the same bits.
-//   NC = 512 (cluster 1 or 2): large batches; an activation tile is loaded once per 512 columns.
-//   NC = 128 (cluster 4 or 8): small batches (streaming, the 1024-segment step): four times as many CTAs, each
-//                              with a quarter of the MMA chain, because a layer's latency is one CTA's MMA time.
+// Up to kSmallBatchRows rows (streaming, the 1024-segment step), tc_linear_ln_kernel: one CTA owns 128 rows x 128
+// output columns in tensor memory (thread <-> TMEM lane <-> row in the epilogue), and the N / 128 CTAs that share a row
+// block form a cluster (4 or 8) which exchanges the per-row LayerNorm statistics - and, in the last layer, the partial
+// 7 logits - through distributed shared memory, always combined in rank order so every CTA sees the same bits.  A
+// layer's latency there is one CTA's MMA chain, hence many short CTAs.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue.
 // Operands are staged by TMA into 128-byte-swizzled K-major tiles.
+// Above kSmallBatchRows rows: the persistent CTA-pair kernel of msa_fusion_pair.cuh (tcgen05.mma.cta_group::2).
 #include <cooperative_groups.h>
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -99,12 +98,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(reinterpret_cast<uint64_t>(map)), "r"(s2u(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// shared -> global tile store (bulk async group of the issuing thread)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(map)),
-               "r"(s2u(src)), "r"(c0), "r"(c1)
-               : "memory");
-}
 // K-major, 128-byte swizzle: 8-row groups of 1024 bytes (SBO), one swizzle atom along K (LBO unused)
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_ptr) {
   uint64_t d = 0;
@@ -139,6 +132,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load in two steps, so that the next chunk's load is in flight while the current chunk is stored: the wait
+// names the registers as in/out operands, which keeps every use of them behind it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float* v) {       // 64 consecutive columns: two loads, one wait
   uint32_t r[64];
 #pragma unroll
@@ -162,7 +177,7 @@ __device__ __forceinline__ void tmem_ld32x2(uint32_t taddr, float* v) {       //
 // Up to three independent layers of the same shape class (the per-modality branches of fusion_model.py:44-86)
 // share one launch: blockIdx.z selects the layer.
 struct TcBatch {
-  CUtensorMap maps[3][6];   // A_hi, A_lo, W_hi, W_lo, out_hi, out_lo (the last two: 64-column x 32-row store boxes)
+  CUtensorMap maps[3][4];   // A_hi, A_lo, W_hi, W_lo
   TcEpilogue ep[3];
   int trace_slot;           // MSA_TC_TRACE builds: which launch of the forward this is
 };
@@ -172,16 +187,9 @@ struct TcBatch {
 #ifdef MSA_TC_TRACE
 constexpr int kTraceSlots = 4, kTraceEvents = 8, kTraceCtas = 4096;
 __device__ long long g_tc_trace[kTraceSlots][kTraceEvents][kTraceCtas];
-#define MSA_TRACE(ev)                                                                                              \
-  do {                                                                                                             \
-    const unsigned cta_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);                          \
-    if (cta_ < (unsigned)kTraceCtas && batch.trace_slot < kTraceSlots) g_tc_trace[batch.trace_slot][ev][cta_] = clock64(); \
-  } while (0)
-#else
-#define MSA_TRACE(ev) do { } while (0)
 #endif
 
-// NC: output columns per CTA (512 or 128); CL: CTAs per cluster along grid.y = n_total / NC;
+// NC: output columns per CTA (128 in the product; the shape traits also cover 256 / 512); CL: CTAs per cluster along grid.y = n_total / NC;
 // kFinal: fuse Linear(512 -> 7) + argmax behind the ReLU.
 template <int NC, int CL, bool kFinal>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __grid_constant__ TcBatch batch) {
@@ -423,30 +431,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_linear_ln_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------ large batches: CTA pairs
-// Above kSmallBatchRows rows the layer runs as tcgen05.mma.cta_group::2: two CTAs on the two SMs of a TPC own 256
-// rows x 512 columns; each stages ITS 128 rows of the activations and HALF of the 256 weight rows of an MMA
-// (hi + lo: 64 KB per stage, three stages) and the leader issues M = 256, N = 256 MMAs that read both CTAs' shared
-// memory and write both CTAs' tensor memory.  Against one CTA per 128 x 512 tile this halves the weight bytes every SM
-// pulls from L2 and cuts the shared-memory traffic per MMA k-step (operand reads + TMA writes) from 60 KB to 40 KB
-// per 384 tensor-pipe cycles - the single-CTA form asks for 156 B/clk of a 128 B/clk shared memory.
-// Barriers: both CTAs' TMA loads complete on the LEADER's full barrier (it expects the bytes of both); the leader's
-// tcgen05.commit multicasts to the empty (and accumulator-full) barriers of both CTAs.
-// Epilogue: all eight warps (the producer / MMA / allocator warps join once the mainloop has drained): warps 4-7 take
-// columns 0-255 of their 32 rows, warps 0-3 columns 256-511; the 2 (x CLN column blocks of the cluster) partial
-// (mean, M2) per row are combined with Chan's formula in a fixed order.
-struct PairTail {
-  uint64_t full[3], empty[3], accum_full;
-  uint32_t tmem_base, pad;
-  float2 stats[2][BLOCK_M];
-  float part7[2][BLOCK_M][8];
-  float bias[512], gamma[512], beta[512];
-  float w8[kOut * 512];
-  float b8[8];
-};
+// Above kSmallBatchRows rows a layer runs as tcgen05.mma.cta_group::2 in a persistent kernel (msa_fusion_pair.cuh): two
+// CTAs on the two SMs of a TPC own 256 rows x 512 columns; each stages ITS 128 rows of the activations and HALF of the
+// 256 weight rows of an MMA (hi + lo: 64 KB per stage, three stages) and the leader issues M = 256, N = 256 MMAs that
+// read both CTAs' shared memory and write both CTAs' tensor memory.  Against one CTA per 128 x 512 tile this halves the
+// weight bytes every SM pulls from L2 and cuts the shared-memory traffic per MMA k-step (operand reads + TMA writes)
+// from 60 KB to 40 KB per 384 tensor-pipe cycles - the single-CTA form asks for 156 B/clk of a 128 B/clk shared memory.
 constexpr int kPairTileB = 128 * BLOCK_K * 2;                            // this CTA's half of a 256-row weight tile: 16 KB
 constexpr int kPairStageBytes = 2 * kTileA + 2 * kPairTileB;             // 64 KB
 constexpr int kPairStages = 3;
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + (int)sizeof(PairTail) + 1024;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -477,257 +470,6 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
                : "memory");
 }
 
-// CLN: column blocks of 512 per row block (cluster = 2 x CLN CTAs: the pair along x, the column blocks along y)
-template <int CLN, bool kFinal>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_pair_linear_ln_kernel(const __grid_constant__ TcBatch batch) {
-  constexpr int NC = 512, N_SUB = 256;
-  const CUtensorMap& tmA_hi = batch.maps[blockIdx.z][0];
-  const CUtensorMap& tmA_lo = batch.maps[blockIdx.z][1];
-  const CUtensorMap& tmW_hi = batch.maps[blockIdx.z][2];
-  const CUtensorMap& tmW_lo = batch.maps[blockIdx.z][3];
-  const TcEpilogue& ep = batch.ep[blockIdx.z];
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  PairTail* tail = reinterpret_cast<PairTail*>(smem + kPairStages * kPairStageBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t crank = cluster_ctarank();                              // x + 2 y
-  const uint32_t px = crank & 1u, py = crank >> 1;                       // rank in the pair, column block
-  const bool leader = px == 0;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * NC;
-  const int k_blocks = ep.k_blocks;
-  cg::cluster_group cluster = cg::this_cluster();
-  if (threadIdx.x == 0) MSA_TRACE(0);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kPairStages; ++s) { mbar_init(&tail->full[s], 1); mbar_init(&tail->empty[s], 1); }
-    mbar_init(&tail->accum_full, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) {                                                       // the same warp of both CTAs allocates for the pair
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(&tail->tmem_base)), "r"(NC));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster.sync();                                                        // the peer's barriers exist before anything arrives on them
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tail->tmem_base;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (threadIdx.x == 0) MSA_TRACE(1);
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one thread of EACH CTA)
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int ns = 0; ns < NC / N_SUB; ++ns) {
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&tail->empty[stage], phase ^ 1);
-          unsigned char* st = smem + stage * kPairStageBytes;
-          if (leader) mbar_expect_tx(&tail->full[stage], 2 * kPairStageBytes);
-          const uint32_t bar = mapa_shared(s2u(&tail->full[stage]), crank & ~1u);
-          const int wrow = n0 + ns * N_SUB + (int)px * (N_SUB / 2);
-          tma_load_2d_pair(&tmA_hi, bar, st, kb * BLOCK_K, m0);
-          tma_load_2d_pair(&tmA_lo, bar, st + kTileA, kb * BLOCK_K, m0);
-          tma_load_2d_pair(&tmW_hi, bar, st + 2 * kTileA, kb * BLOCK_K, wrow);
-          tma_load_2d_pair(&tmW_lo, bar, st + 2 * kTileA + kPairTileB, kb * BLOCK_K, wrow);
-          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread of the leader)
-    if (lane == 0 && leader) {
-      // kind::f16: D fp32, A/B bf16, both K-major, M = 256 over the pair, N = 256
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_SUB >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
-      const uint16_t pair_mask = (uint16_t)(3u << (2 * py));
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int ns = 0; ns < NC / N_SUB; ++ns) {
-        const uint32_t tmem_d = tmem_base + ns * N_SUB;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&tail->full[stage], phase);
-          if (ns == 0 && kb == 0) MSA_TRACE(2);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          unsigned char* st = smem + stage * kPairStageBytes;
-          const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + kTileA);
-          const uint64_t w_hi = umma_desc_sw128(st + 2 * kTileA), w_lo = umma_desc_sw128(st + 2 * kTileA + kPairTileB);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-            umma_bf16_pair(tmem_d, a_hi + adv, w_hi + adv, idesc, (kb | k) != 0);
-            umma_bf16_pair(tmem_d, a_lo + adv, w_hi + adv, idesc, 1);
-            umma_bf16_pair(tmem_d, a_hi + adv, w_lo + adv, idesc, 1);
-          }
-          umma_commit_pair(&tail->empty[stage], pair_mask);               // frees the stage in both CTAs
-          if (++stage == kPairStages) { stage = 0; phase ^= 1; }
-        }
-      }
-      umma_commit_pair(&tail->accum_full, pair_mask);
-      MSA_TRACE(3);
-    }
-    __syncwarp();
-  } else if (warp >= 4) {
-    const int et = threadIdx.x - 128;
-    for (int i = et; i < NC; i += 128) {
-      tail->bias[i] = ep.bias[n0 + i];
-      tail->gamma[i] = ep.gamma[n0 + i];
-      tail->beta[i] = ep.beta[n0 + i];
-    }
-    if (kFinal) {
-      for (int i = et; i < kOut * NC; i += 128) tail->w8[i] = ep.w8[(i / NC) * ep.n_total + n0 + (i % NC)];
-      if (et < kOut) tail->b8[et] = ep.b8[et];
-    }
-  }
-  __syncthreads();                                                       // epilogue constants staged; every warp is an epilogue warp from here
-
-  // ------------------------------------------------------------------ epilogue pass 1: row statistics of this thread's 256 columns
-  const int q = warp & 3, half = (warp < 4) ? 1 : 0;
-  const int row_in_tile = q * 32 + lane;
-  const int c0 = half * (NC / 2);
-  const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-  mbar_wait(&tail->accum_full, 0);
-  if (threadIdx.x == 128) MSA_TRACE(4);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  {
-    float sum = 0.0f, sumsq = 0.0f, shift = 0.0f;
-    for (int c = c0; c < c0 + NC / 2; c += 32) {
-      float v[32];
-      tmem_ld32(trow + c, v);
-      if (c == c0) shift = v[0] + tail->bias[c0];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float x = v[i] + tail->bias[c + i] - shift;
-        sum += x;
-        sumsq = fmaf(x, x, sumsq);
-      }
-    }
-    const float dm = sum * (1.0f / (float)(NC / 2));
-    tail->stats[half][row_in_tile] = make_float2(shift + dm, fmaxf(sumsq - sum * dm, 0.0f));     // (mean_i, M2_i) of 256 columns
-  }
-  if (threadIdx.x == 128) MSA_TRACE(5);
-  if (CLN > 1) cluster.sync();
-  else __syncthreads();
-
-  // ------------------------------------------------------------------ epilogue pass 2: normalise, ReLU, store / project
-  {
-    constexpr int NP = 2 * CLN;                                          // partials per row, each over 256 columns
-    float mi[NP], msum = 0.0f, m2 = 0.0f;
-#pragma unroll
-    for (int r = 0; r < CLN; ++r) {
-      const float2* peer = (CLN > 1) ? cluster.map_shared_rank(&tail->stats[0][0], (int)px + 2 * r) : &tail->stats[0][0];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float2 o = peer[h * BLOCK_M + row_in_tile];
-        mi[2 * r + h] = o.x;
-        msum += o.x;
-        m2 += o.y;
-      }
-    }
-    const float mean = msum * (1.0f / (float)NP);
-    float spread = 0.0f;
-#pragma unroll
-    for (int r = 0; r < NP; ++r) spread = fmaf(mi[r] - mean, mi[r] - mean, spread);
-    const float var = (m2 + (float)(NC / 2) * spread) / (float)ep.n_total;
-    const float rstd = rsqrtf(var + 1e-5f);
-    const int row = m0 + row_in_tile;
-    float acc[kOut];
-#pragma unroll
-    for (int j = 0; j < kOut; ++j) acc[j] = 0.0f;
-    if (kFinal) {
-      for (int c = c0; c < c0 + NC / 2; c += 32) {
-        float v[32];
-        tmem_ld32(trow + c, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float y = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
-          y = fmaxf(y, 0.0f);
-#pragma unroll
-          for (int j = 0; j < kOut; ++j) acc[j] = fmaf(y, tail->w8[j * NC + c + i], acc[j]);
-        }
-      }
-    } else {
-      // The (hi, lo) bf16 rows leave through shared memory and TMA: a thread owns a ROW, so direct stores would touch
-      // 32 different 128-byte lines per instruction (measured: 31,000 cycles of this pass per CTA, against 51,000 of MMA).
-      // Per warp and 64 columns: every lane writes its row's 128 bytes of hi and of lo into a 128-byte-swizzled 32-row
-      // tile (the pipeline stages are free by now), lane 0 issues one tensor store per tile; two tiles in flight.
-      unsigned char* stg = smem + warp * 16384;
-      const CUtensorMap* tmO_hi = &batch.maps[blockIdx.z][4];
-      const CUtensorMap* tmO_lo = &batch.maps[blockIdx.z][5];
-      int buf = 0;
-      for (int cc = c0; cc < c0 + NC / 2; cc += 64) {
-        unsigned char* sh = stg + buf * 8192;
-        unsigned char* sl = sh + 4096;
-        if (cc >= c0 + 128) {                                            // this buffer's previous tile has been read out
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
-        }
-#pragma unroll
-        for (int hc = 0; hc < 2; ++hc) {
-          const int c = cc + 32 * hc;
-          float v[32];
-          tmem_ld32(trow + c, v);
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float y0 = (v[i] + tail->bias[c + i] - mean) * rstd * tail->gamma[c + i] + tail->beta[c + i];
-            float y1 = (v[i + 1] + tail->bias[c + i + 1] - mean) * rstd * tail->gamma[c + i + 1] + tail->beta[c + i + 1];
-            y0 = fmaxf(y0, 0.0f);
-            y1 = fmaxf(y1, 0.0f);
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
-            const float2 hf = __bfloat1622float2(h2);
-            const __nv_bfloat162 l2 = __floats2bfloat162_rn(y0 - hf.x, y1 - hf.y);
-            hi[i / 2] = *reinterpret_cast<const uint32_t*>(&h2);
-            lo[i / 2] = *reinterpret_cast<const uint32_t*>(&l2);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int off = lane * 128 + (((hc * 4 + j) ^ (lane & 7)) << 4);
-            *reinterpret_cast<uint4*>(sh + off) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            *reinterpret_cast<uint4*>(sl + off) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(tmO_hi, sh, ep.col_off + n0 + cc, m0 + q * 32);
-          tma_store_2d(tmO_lo, sl, ep.col_off + n0 + cc, m0 + q * 32);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        buf ^= 1;
-      }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      __syncwarp();
-    }
-    if (kFinal) {                                                        // CLN == 1: the two column halves of a row meet in shared memory
-#pragma unroll
-      for (int j = 0; j < kOut; ++j) tail->part7[half][row_in_tile][j] = acc[j];
-      __syncthreads();
-      if (half == 0 && row < ep.m_valid) {
-        int best = 0;
-        float bv = 0.0f;
-#pragma unroll
-        for (int j = 0; j < kOut; ++j) {
-          const float l = tail->part7[0][row_in_tile][j] + tail->part7[1][row_in_tile][j] + tail->b8[j];
-          ep.logits[(size_t)row * kOut + j] = l;
-          if (j == 0 || l > bv) { bv = l; best = j; }
-        }
-        if (ep.argmax) ep.argmax[row] = best;
-      }
-    }
-  }
-  if (threadIdx.x == 128) MSA_TRACE(6);
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster.sync();                                                        // nobody frees tensor memory or exits while the pair still works
-  if (threadIdx.x == 128) MSA_TRACE(7);
-  if (warp == 2) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(NC));
-  }
-}
-
 }  // namespace msa
 #include "msa_fusion_pair.cuh"
 namespace msa {
@@ -742,6 +484,7 @@ struct PrepArgs {
   __nv_bfloat16* lo[3];
   int d[3], kpad[3];
   int B, Bp, nmod;
+  int lane_rows;            // short rows (<= 32 columns): one lane per row (large batches) instead of one warp per row
 };
 
 constexpr int kPrepMaxK = 832;                                           // 783 padded to a multiple of 64
@@ -784,26 +527,77 @@ __device__ __forceinline__ void prep_row(const float* x, const float* gamma, con
   }
 }
 
+// Rows of at most 32 columns (face 27, audio 31): one LANE per row, the whole row in registers, no shuffles; every lane
+// writes its row's 64 (hi) + 64 (lo) zero-padded bf16 as whole 128-byte lines.  (One warp per such row made 16,384
+// eight-warp CTAs of a few instructions each: half of this kernel's 189 us at 65,536 rows.)
+__device__ __forceinline__ void prep_short_row(const float* x, const float* gamma, const float* beta, int d, uint4* hi, uint4* lo) {
+  float v[32];
+  float sum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    v[i] = (i < d) ? x[i] : 0.0f;
+    sum += v[i];
+  }
+  const float mean = sum / (float)d;
+  float sq = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float dd = (i < d) ? v[i] - mean : 0.0f;
+    sq = fmaf(dd, dd, sq);
+  }
+  const float rstd = rsqrtf(sq / (float)d + 1e-5f);
+  uint32_t h[16], l[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float y0 = (i < d) ? (v[i] - mean) * rstd * __ldg(gamma + i) + __ldg(beta + i) : 0.0f;
+    const float y1 = (i + 1 < d) ? (v[i + 1] - mean) * rstd * __ldg(gamma + i + 1) + __ldg(beta + i + 1) : 0.0f;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+    h[i / 2] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    l[i / 2] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    lo[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+    hi[4 + j] = make_uint4(0u, 0u, 0u, 0u);                               // columns 32..63: K padding
+    lo[4 + j] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+static_assert(kFaceK == 64 && kAudioK == 64, "prep_short_row writes 64 padded columns");
+
 __global__ void __launch_bounds__(256, 3) tc_input_prep_kernel(const PrepArgs a) {
-  // the warp's row is normalised with lane-strided columns (coalesced loads), staged as bf16 pairs in shared memory and
-  // written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at a quarter of the HBM rate.
-  // The 27- and 31-column rows of the face and audio branches take the one-group instance, not 25 predicated trips of
-  // the 783-column text rows (they were two thirds of this kernel's instructions: 240 us at 65,536 rows).
+  // a long row (text, 783 columns) is normalised by one warp with lane-strided columns (coalesced loads), staged as bf16
+  // pairs in shared memory and written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at
+  // a quarter of the HBM rate.
   __shared__ __align__(16) __nv_bfloat16 stage[8][2][kPrepMaxK];
   const int m = blockIdx.y;
-  const int w = threadIdx.x >> 5;
-  const int row = blockIdx.x * 8 + w, lane = threadIdx.x & 31;
-  if (row >= a.Bp) return;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = a.d[m], kpad = a.kpad[m];
+  if (d <= 32 && a.lane_rows) {                                           // kpad == 64
+    const int row = (blockIdx.x * 8 + w) * 32 + lane;
+    if (row >= a.Bp) return;
+    uint4* hi = reinterpret_cast<uint4*>(a.hi[m] + (size_t)row * kpad);
+    uint4* lo = reinterpret_cast<uint4*>(a.lo[m] + (size_t)row * kpad);
+    if (row >= a.B) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { hi[j] = make_uint4(0u, 0u, 0u, 0u); lo[j] = make_uint4(0u, 0u, 0u, 0u); }
+      return;
+    }
+    prep_short_row(a.x[m] + (size_t)row * d, a.gamma[m], a.beta[m], d, hi, lo);
+    return;
+  }
+  const int row = blockIdx.x * 8 + w;
+  if (row >= a.Bp) return;
   uint4* hi = reinterpret_cast<uint4*>(a.hi[m] + (size_t)row * kpad);
   uint4* lo = reinterpret_cast<uint4*>(a.lo[m] + (size_t)row * kpad);
   if (row >= a.B) {
     for (int c = lane; c < kpad / 8; c += 32) { hi[c] = make_uint4(0u, 0u, 0u, 0u); lo[c] = make_uint4(0u, 0u, 0u, 0u); }
     return;
   }
-  const float* x = a.x[m] + (size_t)row * d;
-  if (d <= 32) prep_row<1>(x, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);
-  else prep_row<25>(x, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);   // 783 <= 25 * 32
+  if (d <= 32) prep_row<1>(a.x[m] + (size_t)row * d, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);   // small batch: latency, not throughput
+  else prep_row<25>(a.x[m] + (size_t)row * d, a.gamma[m], a.beta[m], d, kpad, lane, stage[w][0], stage[w][1]);         // 783 <= 25 * 32
   __syncwarp();
   const uint4* sh = reinterpret_cast<const uint4*>(stage[w][0]);
   const uint4* sl = reinterpret_cast<const uint4*>(stage[w][1]);
@@ -826,19 +620,17 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 row-major [rows, cols] -> TMA map with box [box_rows, box_cols]: 64 columns with the 128-byte swizzle (operand
-// tiles), or 32 columns with the 64-byte swizzle (the persistent pair kernel's store tiles)
-static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols = BLOCK_K) {
-  if (!base) { std::memset(map, 0, sizeof(*map)); return MSA_OK; }    // the last layer stores no activations
+// bf16 row-major [rows, cols] -> TMA map with box [box_rows, 64 cols], 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return MSA_ERR_BAD_ARGUMENT;
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t box[2] = {BLOCK_K, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? MSA_OK : 1000 + (int)r;
 }
 
@@ -874,28 +666,6 @@ static cudaError_t launch_variant(const TcBatch& batch, int Bp, int N, int count
   cfg.attrs = attr2;
   cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, tc_linear_ln_kernel<NC, CL, kFinal>, batch);
-}
-
-template <int CLN, bool kFinal>
-static cudaError_t launch_pair_variant(const TcBatch& batch, int Bp, int N, int count, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(tc_pair_linear_ln_kernel<CLN, kFinal>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes);
-  if (e != cudaSuccess) return e;
-  if (Bp % (2 * BLOCK_M) != 0 || N != 512 * CLN) return cudaErrorInvalidValue;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(Bp / BLOCK_M, CLN, count);
-  cfg.blockDim = dim3(kTcThreads, 1, 1);
-  cfg.dynamicSmemBytes = kPairSmemBytes;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = CLN;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  return cudaLaunchKernelEx(&cfg, tc_pair_linear_ln_kernel<CLN, kFinal>, batch);
 }
 
 template <int CLN, bool kFinal>
@@ -955,9 +725,6 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     if ((rc = make_map(&batch.maps[i][1], L.a_lo, Bp, L.a_cols, BLOCK_M))) return rc;
     if ((rc = make_map(&batch.maps[i][2], packed + h.hi_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
     if ((rc = make_map(&batch.maps[i][3], packed + h.lo_off[L.gemm], gw.N, gw.Kpad, nsub))) return rc;
-    static const bool persist = !(getenv("MSA_PAIR_MODE") && getenv("MSA_PAIR_MODE")[0] == '0');
-    if ((rc = make_map(&batch.maps[i][4], L.out_hi, Bp, L.ld_out, 32, (!small && persist) ? 32 : BLOCK_K))) return rc;
-    if ((rc = make_map(&batch.maps[i][5], L.out_lo, Bp, L.ld_out, 32, (!small && persist) ? 32 : BLOCK_K))) return rc;
     TcEpilogue& ep = batch.ep[i];
     ep.bias = reinterpret_cast<const float*>(packed + h.f32_off[L.bias_t]);
     ep.gamma = reinterpret_cast<const float*>(packed + h.f32_off[L.gamma_t]);
@@ -975,18 +742,14 @@ static int launch_layers(const LayerLaunch* Ls, int count, int B, int Bp, const 
     ep.argmax = argmax;
   }
   const bool fin = Ls[0].final_layer;
-  static const bool persist = !(getenv("MSA_PAIR_MODE") && getenv("MSA_PAIR_MODE")[0] == '0');
   batch.trace_slot = fin ? 3 : (N == 1024 ? (count > 1 ? 0 : 2) : 1);    // projections, processors, fusion.0, fusion.4
   cudaError_t e;
   if (N == 1024) {
     if (fin) return MSA_ERR_BAD_ARGUMENT;
-    e = small ? launch_variant<128, 8, false>(batch, Bp, N, count, s)
-              : (persist ? launch_pair_persistent<2, false>(batch, Bp, N, count, s) : launch_pair_variant<2, false>(batch, Bp, N, count, s));
+    e = small ? launch_variant<128, 8, false>(batch, Bp, N, count, s) : launch_pair_persistent<2, false>(batch, Bp, N, count, s);
   } else if (N == 512) {
-    if (fin) e = small ? launch_variant<128, 4, true>(batch, Bp, N, count, s)
-                       : (persist ? launch_pair_persistent<1, true>(batch, Bp, N, count, s) : launch_pair_variant<1, true>(batch, Bp, N, count, s));
-    else e = small ? launch_variant<128, 4, false>(batch, Bp, N, count, s)
-                   : (persist ? launch_pair_persistent<1, false>(batch, Bp, N, count, s) : launch_pair_variant<1, false>(batch, Bp, N, count, s));
+    if (fin) e = small ? launch_variant<128, 4, true>(batch, Bp, N, count, s) : launch_pair_persistent<1, true>(batch, Bp, N, count, s);
+    else e = small ? launch_variant<128, 4, false>(batch, Bp, N, count, s) : launch_pair_persistent<1, false>(batch, Bp, N, count, s);
   } else {
     return MSA_ERR_BAD_ARGUMENT;
   }
@@ -1014,6 +777,7 @@ int fusion_forward_tc(const float* face, const float* audio, const float* text, 
   pa.d[0] = kFaceDim; pa.d[1] = kAudioDim; pa.d[2] = kTextDim;
   pa.kpad[0] = kFaceK; pa.kpad[1] = kAudioK; pa.kpad[2] = kTextK;
   pa.B = B; pa.Bp = Bp; pa.nmod = three ? 3 : 2;
+  pa.lane_rows = B > kSmallBatchRows;
   tc_input_prep_kernel<<<dim3((Bp + 7) / 8, pa.nmod), 256, 0, s>>>(pa);
   note_launches(1);
 

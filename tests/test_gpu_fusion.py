@@ -175,11 +175,18 @@ def test_full_size_fusion_batch_65536():
     assert np.abs(got - ref).max() < 1e-3, np.abs(got - ref).max()
     assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
     assert torch.equal(at.long(), lt.argmax(1))
-    # batch == loop of rows: bit-identical within a kernel variant (512 columns per CTA above 4096 rows, 128 below:
-    # the LayerNorm statistics are then summed from 4-8 partials instead of 1-2), within rounding across variants
+    # batch == loop of rows: bit-identical within a kernel variant (persistent CTA pairs, 512 columns per CTA, above 4096
+    # rows; 128-column CTAs below: the LayerNorm statistics are then combined from different partials), within rounding
+    # across variants
     big = torch.from_numpy(np.sort(np.random.default_rng(6).choice(n, 5000, replace=False))).to(dev)
     lb, _ = m0.fused_with_argmax(fd[big].contiguous(), ad[big].contiguous(), td[big].contiguous())
     assert torch.equal(lb, lt[big])
+    # face + audio only (fusion2) through the CTA-pair kernels: 5000 rows (padded to 5120), a sample against the fp64 oracle
+    l2m, a2m = m0.fused_with_argmax(fd[big].contiguous(), ad[big].contiguous(), None)
+    bi = big.cpu().numpy()[:512]
+    ref2 = fu.fuse_face_audio(sd, f[bi], a[bi])
+    assert np.abs(l2m[:512].cpu().numpy() - ref2).max() < 1e-3
+    assert torch.equal(a2m.long(), l2m.argmax(1))
     sub = torch.from_numpy(np.sort(idx[:300])).to(dev)
     ls, _ = m0.fused_with_argmax(fd[sub].contiguous(), ad[sub].contiguous(), td[sub].contiguous())
     assert (ls - lt[sub]).abs().max().item() < 2e-5
@@ -372,7 +379,7 @@ def test_streaming_staged_push_and_buffer_growth():
         check(i, o)
 
 
-@pytest.mark.parametrize("n", [300, 5000], ids=["128-column tiles", "512-column tiles"])
+@pytest.mark.parametrize("n", [300, 5000], ids=["128-column tiles", "CTA-pair tiles"])
 def test_layernorm_rows_with_mean_far_from_zero(n):
     """A trained checkpoint can have |row mean| >> row sigma in front of a LayerNorm (large Linear biases): the fused
     epilogue's statistics (shifted sums + Chan combine across the cluster) must not lose the variance there.  Biases
