@@ -93,7 +93,7 @@ inline void packed_layout(PackedHeader& h) {
   h.total_bytes = off;
 }
 
-constexpr int kSmallBatchRows = 4096;                      // at or below: one CTA per 128 rows x 128 columns; above: CTA pairs per 256 rows x 512 columns
+constexpr int kSmallBatchRows = 3072;                      // at or below: one CTA per 128 rows x 128 columns; above: CTA pairs per 256 rows x 512 columns (measured crossover: 197 vs 208 us at 3072 rows, 251 vs 216 us at 4096; profiles/r2_v204_fusion_threshold.txt)
 
 // Activation workspace for batch B (rows padded to one MMA tile of rows: 128, or 256 where CTA pairs run).
 struct Workspace {

@@ -175,7 +175,7 @@ def test_full_size_fusion_batch_65536():
     assert np.abs(got - ref).max() < 1e-3, np.abs(got - ref).max()
     assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
     assert torch.equal(at.long(), lt.argmax(1))
-    # batch == loop of rows: bit-identical within a kernel variant (persistent CTA pairs, 512 columns per CTA, above 4096
+    # batch == loop of rows: bit-identical within a kernel variant (persistent CTA pairs, 512 columns per CTA, above 3072
     # rows; 128-column CTAs below: the LayerNorm statistics are then combined from different partials), within rounding
     # across variants
     big = torch.from_numpy(np.sort(np.random.default_rng(6).choice(n, 5000, replace=False))).to(dev)
