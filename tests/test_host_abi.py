@@ -55,6 +55,11 @@ def test_capacity_queries_without_device(built):
     assert l.msa_fusion_num_tensors() == 42
     assert l.msa_strerror(0) == b"ok" and b"too long" in l.msa_strerror(-2)
     assert l.msa_fusion_workspace_bytes(1024) > 0 and l.msa_fusion_packed_bytes() > 4 * 5_600_000
+    # the activation workspace grows with the batch, also across the 3072-row switch from 128-row tiles (one CTA) to
+    # 256-row tiles (CTA pairs): a workspace sized for the largest batch serves every smaller one
+    sizes = [l.msa_fusion_workspace_bytes(b) for b in (1, 128, 129, 3072, 3073, 3200, 4096, 5000, 65536)]
+    assert all(a <= b for a, b in zip(sizes, sizes[1:])), sizes
+    assert l.msa_fusion_workspace_bytes(3073) == l.msa_fusion_workspace_bytes(3328)      # both pad to 13 tiles of 256 rows
 
 
 def test_state_dict_matches_reference_layout(built):
