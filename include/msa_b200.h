@@ -71,7 +71,8 @@ int msa_features_smem_bytes(int T, int cluster_size);
  *           [64:80] diagnostics (top_db max, residual mean/std/max, energies, counts, clamped-pass flag, min dB,
  *           candidate level, clamp flag)
  *   dbg_mfcc [B, T/200+1, 13] out or NULL: the MFCC matrix (frames x coefficients)
- *   cluster_size 0 = auto, else 1/2/4/8
+ *   cluster_size 0 = auto, else 1/2/4/8/16 (16 is a non-portable cluster size: MSA_ERR_BAD_ARGUMENT where the device does
+ *   not co-schedule 16 CTAs of the kernel; auto picks it for a handful of segments only)
  */
 int msa_features_f32(const float* wav, int B, int T, const float* emo8, float* feat31, float* detail,
                      float* dbg_mfcc, int flags, int parts, int cluster_size, void* stream);

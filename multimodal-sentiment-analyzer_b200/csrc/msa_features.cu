@@ -78,12 +78,49 @@ int features_cluster_size(int T) {
   return 0;
 }
 
+// Largest cluster the device schedules for this kernel: 16 CTAs (a non-portable size, asked for explicitly) where a GPC
+// takes them, else 8.  Asked once per device and input type.
+template <class InT>
+static int max_cluster_size(int T) {
+  static int cached[64] = {0}, cached_smem[64] = {0};                   // the answer depends on the CTA's shared memory
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 8;
+  const FeatLayout lay = feat_layout(T, 16, feat_threads() / 32);
+  if (cached[dev] == 0 || cached_smem[dev] != lay.total) {
+    cached[dev] = 8;
+    cached_smem[dev] = lay.total;
+    auto kern = features_kernel<InT>;
+    if (lay.total <= kMaxSmem && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.total) == cudaSuccess) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(16, 1, 1);
+      cfg.blockDim = dim3(feat_threads(), 1, 1);
+      cfg.dynamicSmemBytes = lay.total;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 16;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n >= 1) cached[dev] = 16;
+    }
+    (void)cudaGetLastError();
+  }
+  return cached[dev];
+}
+
 // Few segments (streaming: B = 1) spread over more CTAs to cut latency; large batches use the smallest
 // cluster so that the quad lists per CTA stay long.
+template <class InT>
 static int auto_cluster_size(int B, int T) {
   int c = features_cluster_size(T);
   if (c == 0) return 0;
-  while (c < 8 && (long long)B * c * 2 <= 2 * sm_count()) c *= 2;      // up to two CTAs per SM
+  // 16 CTAs per segment pay for a handful of segments only (measured per launch: 1 segment 52.6 -> 47.4 us, 4 segments
+  // 53.4 -> 49.0, 8 segments 53.6 = 53.5, 16 segments 67 -> 97: profiles/r2_v204_tail_probe.json)
+  const int cmax = ((long long)B * 16 * 2 <= sm_count()) ? max_cluster_size<InT>(T) : 8;
+  while (c < cmax && (long long)B * c * 2 <= 2 * sm_count()) c *= 2;   // up to two CTAs per SM
   return c;
 }
 
@@ -105,8 +142,9 @@ static int launch_features(const InT* wav, int B, int T, const float* emo8, floa
   if (B < 0 || T < 1) return MSA_ERR_BAD_ARGUMENT;
   if (B == 0) return MSA_OK;                                   // an empty batch has no buffers to check
   if (!wav || !feat31) return MSA_ERR_BAD_ARGUMENT;
-  int c = cluster_size ? cluster_size : auto_cluster_size(B, T);
-  if (c != 1 && c != 2 && c != 4 && c != 8) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
+  int c = cluster_size ? cluster_size : auto_cluster_size<InT>(B, T);
+  if (c != 1 && c != 2 && c != 4 && c != 8 && c != 16) return c == 0 ? MSA_ERR_UNSUPPORTED_LENGTH : MSA_ERR_BAD_ARGUMENT;
+  if (c == 16 && max_cluster_size<InT>(T) < 16) return MSA_ERR_BAD_ARGUMENT;   // this device does not co-schedule 16 CTAs of this kernel
   // torch.stft's reflect padding needs T > n_fft/2: below that the reference's method raises and
   // returns its default, which is what a cleared part bit produces.
   if (T <= kNfftP / 2) parts &= ~kPartPitch;

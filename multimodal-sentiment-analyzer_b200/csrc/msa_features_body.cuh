@@ -150,7 +150,7 @@ FeatLayout feat_layout(int T, int nranks, int nwarps) {
   l.atoms_cap = 8 * ((((T + kGroup - 1) / kGroup) + nranks - 1) / nranks);
   int buf = nwarps * kWarpBufBytes;
   // rank 0 gathers all energy atoms and every rank's Partials there at the end
-  const int gather = (((T / kAtom + 8) * 4 + 15) & ~15) + 8 * (int)sizeof(Partials);
+  const int gather = (((T / kAtom + 8) * 4 + 15) & ~15) + (nranks > 8 ? nranks : 8) * (int)sizeof(Partials);
   if (buf < gather) buf = gather;
   l.buf_off = take(buf);
   // the MFCC rows share their region with the "pitch" phase's per-warp copy of the quad's input samples

@@ -39,7 +39,8 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   struct Case { int B, c; };
   const Case cases[] = {{148, 1}, {296, 1}, {444, 1}, {592, 1}, {740, 1}, {888, 1}, {960, 1}, {1024, 1}, {1184, 1}, {1480, 1},
-                        {136, 1}, {136, 2}, {136, 4}, {68, 2}, {68, 4}, {74, 4}, {148, 2}};
+                        {136, 1}, {136, 2}, {136, 4}, {68, 2}, {68, 4}, {74, 4}, {148, 2},
+                        {1, 4}, {1, 8}, {1, 16}, {4, 8}, {4, 16}, {8, 8}, {8, 16}, {16, 8}, {16, 16}, {1, 0}, {8, 0}, {16, 0}};
   printf("{\"cases\": [");
   bool first = true;
   for (const Case& cs : cases) {

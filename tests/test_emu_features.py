@@ -75,7 +75,7 @@ def check_against_oracle(det, feat, x, emo=None, rel=1e-3, floor=1e-6):
     assert np.all(np.abs(feat - row) <= rel * np.abs(row) + floor)
 
 
-@pytest.mark.parametrize("nranks,nwarps", [(1, 8), (2, 4), (4, 8), (8, 2), (1, 16)])
+@pytest.mark.parametrize("nranks,nwarps", [(1, 8), (2, 4), (4, 8), (8, 2), (16, 8), (1, 16)])
 def test_seeded_segment_all_cluster_sizes(emu, nranks, nwarps):
     x = synth.pcm_to_f32(synth.segment_pcm(1234))
     feat, det, dbg = run(emu, x[None], nranks, nwarps)
@@ -165,7 +165,7 @@ def test_results_do_not_depend_on_the_partition(emu, name):
         x = synth.pcm_to_f32(synth.segment_pcm(1234)) if name == "seg1234" else synth.adversarial_cases()[name]
     ref = None
     paths = set()
-    for nranks, nwarps, scratch in ((1, 8, False), (2, 8, False), (8, 8, True), (1, 2, False), (4, 3, True), (1, 2, True), (1, 8, True)):
+    for nranks, nwarps, scratch in ((1, 8, False), (2, 8, False), (8, 8, True), (16, 8, False), (1, 2, False), (4, 3, True), (1, 2, True), (1, 8, True)):
         feat, det, dbg = run(emu, x[None], nranks, nwarps, scratch=scratch)
         paths.add((det[0, 78], det[0, 75]))
         cur = (feat.copy(), det[:, :63].copy(), dbg.copy())

@@ -67,7 +67,7 @@ def test_golden_seeded_segments(ana, golden_features):
         close(row, g["analyze_rows"][i], what="analyze row")
 
 
-@pytest.mark.parametrize("cluster,T", [(1, 80000), (2, 80000), (4, 80000), (8, 80000), (1, 16000), (2, 16000), (2, 30001), (0, 80000), (0, 160000)])
+@pytest.mark.parametrize("cluster,T", [(1, 80000), (2, 80000), (4, 80000), (8, 80000), (16, 80000), (16, 8000), (1, 16000), (2, 16000), (2, 30001), (0, 80000), (0, 160000)])
 def test_cluster_sizes_agree_with_oracle(ana, cluster, T):
     x = synth.pcm_to_f32(synth.segment_pcm(1234, T))[None]
     _, det, mf = _detail(ana, x, cluster=cluster)
@@ -208,12 +208,12 @@ def test_empty_batch_and_bad_arguments(ana):
     assert lib.msa_features_f32(_lib.ptr(w), 0, 80000, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == 0     # B = 0: nothing to do
     assert lib.msa_features_f32(None, 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == -1
     assert lib.msa_features_f32(_lib.ptr(w), 1, 0, None, _lib.ptr(feat), None, None, 1, 7, 0, None) == -1
-    assert lib.msa_features_f32(_lib.ptr(w), 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 3, None) == -1    # cluster size must be 1/2/4/8
+    assert lib.msa_features_f32(_lib.ptr(w), 1, 80000, None, _lib.ptr(feat), None, None, 1, 7, 3, None) == -1    # cluster size must be 1/2/4/8/16
     assert ana.analyze_batch(torch.zeros(0, 80000, device=ana.device)).shape == (0, 31)
 
 
 def test_results_do_not_depend_on_cluster_size(ana):
-    """One segment per CTA, or split over 2 / 4 / 8 CTAs (what small batches and streaming use): the same bits,
+    """One segment per CTA, or split over 2 / 4 / 8 / 16 CTAs (what small batches and streaming use): the same bits,
     whichever top_db path (patch list / clamped pass) each CTA takes.  Column 8 ("pitch") is the rounding residue of
     the STFT -> ISTFT round trip and depends on the summation tree (|v| <= 1e-6 either way)."""
     rng = np.random.default_rng(5)
@@ -224,7 +224,7 @@ def test_results_do_not_depend_on_cluster_size(ana):
     x = np.stack([synth.pcm_to_f32(synth.segment_pcm(1234)), flip, adv["tone_220"], adv["half_silence"], adv["white_0p1"]])
     cols = [c for c in range(63) if c != 8]
     ref = None
-    for c in (1, 2, 4, 8):
+    for c in (1, 2, 4, 8, 16):                             # 16: a non-portable cluster size, used where the device schedules it
         feat, det, mf = _detail(ana, x, cluster=c)
         if ref is None:
             ref = (feat, det, mf)
@@ -264,7 +264,7 @@ def test_workspace_path_equals_recompute_path(ana):
     B, T = w.shape
     ws = torch.full((ana._lib.msa_features_workspace_bytes(B, T) // 4,), float("nan"), device=ana.device)
     feat = torch.empty(B, 31, device=ana.device); det = torch.empty(B, 96, device=ana.device); mf = torch.empty(B, T // 200 + 1, 13, device=ana.device)
-    for cluster in (1, 2, 8):
+    for cluster in (1, 2, 8, 16):
         rc = ana._lib.msa_features_ws_f32(_lib.ptr(w), B, T, None, _lib.ptr(feat), _lib.ptr(det), _lib.ptr(mf), 1, 7, cluster,
                                           _lib.ptr(ws), ws.numel() * 4, _lib.current_stream_ptr(ana.device))
         assert rc == 0
