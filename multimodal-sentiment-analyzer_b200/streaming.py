@@ -21,9 +21,9 @@ class StreamingWindow:
     `pos + window`, so the most recent `window` samples are always one CONTIGUOUS slice
     ring[pos : pos + window] (pos = next write position) and no on-device slide is needed.
 
-    Per hop the device work is: one 16 KB host->device copy from a pinned staging buffer, one 16 KB device
-    copy for the mirror, the feature kernel (one segment spread over a cluster of 8 CTAs), the fusion chain
-    (5 launches) and a 32-byte read-back.  A hop is launch-latency bound, so once the window is full the whole
+    Per hop the device work is: one host->device copy from a pinned staging buffer (16 KB of PCM and the face / text
+    rows), one copy of the chunk into the ring and its mirror, the feature kernel (one segment spread over a cluster of
+    16 CTAs), the fusion chain (5 launches) and a 32-byte read-back.  A hop is launch-latency bound, so once the window is full the whole
     sequence is captured into one CUDA graph per ring position (window / hop of them) and replayed: one
     graph launch per chunk instead of ~10 stream operations.  ``use_graph=False`` keeps the eager path."""
 
@@ -77,12 +77,27 @@ class StreamingWindow:
         if self._g is None:
             dev = self.device
             lib = self.analyzer._lib
-            self._g = {"stage": torch.empty(self.hop, dtype=torch.int16).pin_memory(),
-                       "face_h": torch.zeros(1, 27).pin_memory(), "text_h": torch.zeros(1, 783).pin_memory(),
-                       "face": torch.zeros(1, 27, device=dev), "text": torch.zeros(1, 783, device=dev),
-                       "row": torch.zeros(1, 31, device=dev), "logits": torch.zeros(1, 7, device=dev),
-                       "amax": torch.zeros(1, dtype=torch.int32, device=dev),
-                       "out": torch.zeros(8, dtype=torch.float32).pin_memory(),          # 7 logits + argmax (as float)
+            # ONE pinned host buffer and ONE device buffer with the same layout [hop int16 | 27 floats | 783 floats]: a
+            # hop uploads with a single copy (a graph node costs ~2-3 us of dependent latency; there were three);
+            # the fusion kernels read the face / text rows where they land
+            nb_pcm, nb_face, nb_text = 2 * self.hop, 4 * 27, 4 * 783
+            if nb_pcm % 16:
+                raise ValueError("hop must be a multiple of 8 samples")
+            hbuf = torch.zeros(nb_pcm + nb_face + nb_text, dtype=torch.uint8).pin_memory()
+            dbuf = torch.zeros(nb_pcm + nb_face + nb_text, dtype=torch.uint8, device=dev)
+            cut = lambda b, dt, a, n: b[a:a + n].view(dt)
+            obuf = torch.zeros(8, dtype=torch.float32, device=dev)           # 7 logits, then the argmax (int32 bits)
+            out = torch.zeros(8, dtype=torch.float32).pin_memory()
+            self._g = {"hbuf": hbuf, "dbuf": dbuf,
+                       "stage": cut(hbuf, torch.int16, 0, nb_pcm),
+                       "face_h": cut(hbuf, torch.float32, nb_pcm, nb_face).view(1, 27),
+                       "text_h": cut(hbuf, torch.float32, nb_pcm + nb_face, nb_text).view(1, 783),
+                       "pcm": cut(dbuf, torch.int16, 0, nb_pcm),
+                       "face": cut(dbuf, torch.float32, nb_pcm, nb_face).view(1, 27),
+                       "text": cut(dbuf, torch.float32, nb_pcm + nb_face, nb_text).view(1, 783),
+                       "row": torch.zeros(1, 31, device=dev), "obuf": obuf, "logits": obuf[:7].view(1, 7),
+                       "amax": obuf.view(torch.int32)[7:8],
+                       "out": out, "out_argmax": out.view(torch.int32)[7:8],
                        # the window's OWN scratch table for the top_db clamp: a captured graph must not point into the
                        # analyzer's grow-only table, which is replaced when a larger batch comes along
                        "ws": torch.empty(max(1, lib.msa_features_workspace_bytes(1, self.window)), dtype=torch.uint8, device=dev),
@@ -90,20 +105,18 @@ class StreamingWindow:
         return self._g
 
     def _device_hop(self, p: int, has_text: bool):
-        """The device work of one hop at ring position p, on the current stream, with static buffers only: the three
-        uploads (16 KB of PCM, the face row, the text row), the mirror copy, the two kernels' launches and the 32-byte
-        read-back are ALL inside the captured graph, so a hop costs the host one graph launch."""
+        """The device work of one hop at ring position p, on the current stream, with static buffers only: ONE upload
+        (16 KB of PCM, the face row, the text row), one copy of the chunk into the ring and its mirror, the feature
+        kernel, the fusion kernels and ONE 32-byte read-back are all inside the captured graph, so a hop costs the host
+        one graph launch and the device nine dependent nodes (thirteen before: three uploads, the mirror copy, a
+        conversion kernel and two read-backs)."""
         g = self._g
-        self.ring[p:p + self.hop].copy_(g["stage"], non_blocking=True)
-        self.ring[p + self.window:p + self.window + self.hop].copy_(self.ring[p:p + self.hop])
-        g["face"].copy_(g["face_h"], non_blocking=True)
-        if has_text:
-            g["text"].copy_(g["text_h"], non_blocking=True)
+        g["dbuf"].copy_(g["hbuf"], non_blocking=True)
+        self.ring.view(2, self.window)[:, p:p + self.hop].copy_(g["pcm"].expand(2, self.hop))   # chunk and mirror at once
         nxt = (p + self.hop) % self.window
         self.analyzer.analyze_into(self.ring[nxt:nxt + self.window][None, :], g["row"], workspace=g["ws"])
         self.fusion.forward_into(g["face"], g["row"], g["text"] if has_text else None, g["logits"], g["amax"])
-        g["out"][:7].copy_(g["logits"][0], non_blocking=True)
-        g["out"][7:8].copy_(g["amax"].float(), non_blocking=True)
+        g["out"].copy_(g["obuf"], non_blocking=True)
 
     def _graph_for(self, p: int, has_text: bool):
         g = self._static()
@@ -151,14 +164,15 @@ class StreamingWindow:
         self.pos = (p + self.hop) % self.window
         self.n_pushed += 1
         return {"fused_emotion": g["logits"][0], "argmax": g["amax"][0], "audio_row": g["row"][0], "host": g["out"],
-                "done": g["done"]}
+                "host_argmax": g["out_argmax"], "done": g["done"]}
 
     @torch.no_grad()
     def push(self, chunk_pcm: torch.Tensor, face: torch.Tensor, text: Optional[torch.Tensor] = None):
         """chunk_pcm: [hop] int16 on the host.  Returns None until the window is full, then the dict of
         streaming_processor.py:302-320: {"fused_emotion": logits [7], "argmax": int, "audio_row": [31]}.
         On the graph path the results live in static buffers that the next push overwrites, and
-        ``result["host"]`` is a pinned [8] tensor (7 logits, argmax) valid after ``result["done"].synchronize()``
+        ``result["host"]`` is a pinned [8] float tensor (7 logits; the last slot carries the argmax's int32 bits, read it
+        through ``result["host_argmax"]``, an int32 view of that slot) valid after ``result["done"].synchronize()``
         (an event recorded behind the hop's read-back: waiting on it is cheaper than synchronising the stream)."""
         if not self.use_graph or (self.n_pushed + 1) * self.hop < self.window:
             return self._push_eager(chunk_pcm, face, text)
@@ -176,4 +190,4 @@ class StreamingWindow:
         self.pos = (p + self.hop) % self.window
         self.n_pushed += 1
         return {"fused_emotion": g["logits"][0], "argmax": g["amax"][0], "audio_row": g["row"][0], "host": g["out"],
-                "done": g["done"]}
+                "host_argmax": g["out_argmax"], "done": g["done"]}

@@ -320,8 +320,9 @@ def test_streaming_window_equals_offline(use_graph, with_text):
         if o is not None:
             torch.cuda.synchronize()
             host = o["host"].clone() if "host" in o else None
+            host_argmax = o["host_argmax"].clone() if "host_argmax" in o else None
             o = {"audio_row": o["audio_row"].clone(), "fused_emotion": o["fused_emotion"].clone(), "argmax": int(o["argmax"].item()),
-                 "host": host}
+                 "host": host, "host_argmax": host_argmax}
         outs.append(o)
     assert all(o is None for o in outs[:9]) and all(o is not None for o in outs[9:])
     for j, o in enumerate(outs[9:]):
@@ -331,7 +332,7 @@ def test_streaming_window_equals_offline(use_graph, with_text):
         logits, amax = m.fused_with_argmax(faces[i:i + 1], row, texts[i:i + 1] if with_text else None)
         assert torch.equal(o["audio_row"], row[0]) and torch.equal(o["fused_emotion"], logits[0]) and o["argmax"] == int(amax[0].item())
         if o["host"] is not None:
-            assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == o["argmax"]
+            assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host_argmax"][0].item()) == o["argmax"]
 
 
 def test_streaming_staged_push_and_buffer_growth():
@@ -354,7 +355,7 @@ def test_streaming_staged_push_and_buffer_growth():
         row = ana.analyze_batch(seg)
         logits, amax = m.fused_with_argmax(faces[i:i + 1].to(dev), row, texts[i:i + 1].to(dev))
         torch.cuda.synchronize()
-        assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host"][7].item()) == int(amax[0].item()), i
+        assert torch.equal(o["host"][:7], logits[0].cpu()) and int(o["host_argmax"][0].item()) == int(amax[0].item()), i
 
     for i in range(12):
         o = sw.push(torch.from_numpy(pcm[i * 8000:(i + 1) * 8000].copy()), faces[i], texts[i])
