@@ -22,6 +22,9 @@ __global__ void __launch_bounds__(kFeatThreads, 2) features_kernel(const FeatPar
   env.rank = (int)cluster.block_rank();
   env.nranks = (int)cluster.num_blocks();
   env.cluster_id = blockIdx.x / env.nranks;
+  // a kernel launched behind this one with programmatic stream serialization (the first layer of the streaming fusion
+  // path, msa_fusion_rows.cu) may be scheduled now: it fetches its weights and then waits for this grid to complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   features_cta<GpuEnv, InT>(env, P, smem);
 }
 

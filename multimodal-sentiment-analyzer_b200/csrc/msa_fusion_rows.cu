@@ -25,6 +25,7 @@
 namespace msa {
 
 constexpr int kRowsThreads = 128, kRowsWarps = kRowsThreads / 32;
+constexpr int kRowsMaxQ = 1536 / 128, kRowsMaxS = (kTextDim + 31) / 32;     // registers of a preloaded weight row per lane
 
 struct RowJob {
   const float* x;            // raw input rows [B, K], row stride ldx
@@ -51,6 +52,34 @@ __global__ void __launch_bounds__(kRowsThreads) rows_linear_kernel(const RowLaye
   const RowJob& J = L.job[blockIdx.y];
   const int K = J.K, B = L.B, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n0 = blockIdx.x * L.per_cta;
+  // Programmatic dependent launch: this grid is launched while the previous kernel (the feature kernel, or the layer
+  // before) still runs.  Everything that does not depend on it happens first: the warp pulls the weight row of its
+  // first output column (constant, L2-resident between chunks) into registers; then the next layer may be launched, and
+  // only then the warp waits for the previous kernel's results.  A layer's launch latency and its weight fetch are
+  // thereby off the chain of five dependent launches that a streaming hop is.
+  const int nfirst = n0 + warp;
+  const bool vec = (K & 3) == 0;
+  float4 wq[kRowsMaxQ];                                            // vec: K / 128 float4 per lane (K <= 1536)
+  float ws1[kRowsMaxS];                                            // scalar rows (K = 27 / 31 / 783): K / 32 floats per lane
+  const bool pre = n0 < J.N && nfirst < n0 + L.per_cta && nfirst < J.N;
+  if (pre) {
+    const float* w = J.W + (size_t)nfirst * K;
+    if (vec) {
+#pragma unroll
+      for (int i = 0; i < kRowsMaxQ; ++i) {
+        const int k = 4 * lane + 128 * i;
+        wq[i] = (k < K) ? __ldg(reinterpret_cast<const float4*>(w + k)) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < kRowsMaxS; ++i) {
+        const int k = lane + 32 * i;
+        ws1[i] = (k < K) ? __ldg(w + k) : 0.0f;
+      }
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (n0 >= J.N) return;                                          // a job with fewer columns than the widest of the launch
   for (int i = threadIdx.x; i < NB * K; i += kRowsThreads) {
     const int b = i / K, k = i - b * K;
@@ -86,7 +115,31 @@ __global__ void __launch_bounds__(kRowsThreads) rows_linear_kernel(const RowLaye
 #pragma unroll
     for (int b = 0; b < NB; ++b) acc[b] = 0.0f;
     const float* w = J.W + (size_t)n * K;
-    if ((K & 3) == 0) {                                           // rows of W are 16-byte aligned (tensors start on 256 bytes)
+    if (n == nfirst && pre) {                                     // the preloaded row: same products in the same order as below
+      if (vec) {
+#pragma unroll
+        for (int i = 0; i < kRowsMaxQ; ++i) {
+          const int k = 4 * lane + 128 * i;
+          if (k < K) {
+            const float4 q = wq[i];
+#pragma unroll
+            for (int b = 0; b < NB; ++b) {
+              const float4 xv = *reinterpret_cast<const float4*>(xs + b * K + k);
+              acc[b] = fmaf(q.w, xv.w, fmaf(q.z, xv.z, fmaf(q.y, xv.y, fmaf(q.x, xv.x, acc[b]))));
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < kRowsMaxS; ++i) {
+          const int k = lane + 32 * i;
+          if (k < K) {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = fmaf(ws1[i], xs[b * K + k], acc[b]);
+          }
+        }
+      }
+    } else if ((K & 3) == 0) {                                    // rows of W are 16-byte aligned (tensors start on 256 bytes)
 #pragma unroll 4
       for (int k = 4 * lane; k < K; k += 128) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(w + k));
@@ -132,11 +185,21 @@ static void launch_rows(const RowLayer& L, int njobs, int maxN, int maxK, cudaSt
   const dim3 grid((maxN + L.per_cta - 1) / L.per_cta, njobs);
   const int nb = L.B <= 1 ? 1 : (L.B <= 2 ? 2 : (L.B <= 4 ? 4 : 8));
   const size_t smem = (size_t)nb * maxK * sizeof(float);          // <= 8 * 1536 * 4 = 48 KB
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kRowsThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   switch (nb) {
-    case 1: rows_linear_kernel<1><<<grid, kRowsThreads, smem, s>>>(L); break;
-    case 2: rows_linear_kernel<2><<<grid, kRowsThreads, smem, s>>>(L); break;
-    case 4: rows_linear_kernel<4><<<grid, kRowsThreads, smem, s>>>(L); break;
-    default: rows_linear_kernel<8><<<grid, kRowsThreads, smem, s>>>(L); break;
+    case 1: cudaLaunchKernelEx(&cfg, rows_linear_kernel<1>, L); break;
+    case 2: cudaLaunchKernelEx(&cfg, rows_linear_kernel<2>, L); break;
+    case 4: cudaLaunchKernelEx(&cfg, rows_linear_kernel<4>, L); break;
+    default: cudaLaunchKernelEx(&cfg, rows_linear_kernel<8>, L); break;
   }
   note_launches(1);
 }
