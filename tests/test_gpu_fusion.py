@@ -200,6 +200,32 @@ def test_full_size_fusion_batch_65536():
     _model(True, 0)
 
 
+@pytest.mark.parametrize("n", [3073, 3329, 7777, 16385])
+def test_cta_pair_kernels_ragged_batches(n):
+    """Batches just above the switch to the CTA-pair kernels and with ragged last tiles (rows padded to 256): 3-modal and
+    face + audio, against the fp64 oracle on a sample (logits abs 1e-3, arg-max equal) and against the fp32 CUDA-core
+    cross-check on every row; the rows of the padding never reach the outputs (buffers pre-filled with NaN)."""
+    dev = need_gpu()
+    (f, a, t), (fd, ad, td) = _inputs(n, dev)
+    m0, sd = _model(True, 0)
+    idx = np.unique(np.concatenate([np.arange(0, 300), np.arange(n - 300, n), np.random.default_rng(n).choice(n, 400, replace=False)]))
+    for with_text in (True, False):
+        l, am = m0.fused_with_argmax(fd, ad, td if with_text else None)
+        l, am = l.clone(), am.clone()
+        assert tuple(l.shape) == (n, 7) and bool(torch.isfinite(l).all())
+        ref = fu.fuse_all(sd, f[idx], a[idx], t[idx]) if with_text else fu.fuse_face_audio(sd, f[idx], a[idx])
+        got = l[torch.from_numpy(idx).to(dev)].cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-3, (with_text, np.abs(got - ref).max())
+        assert (got.argmax(1) == ref.argmax(1)).mean() >= 0.999
+        assert torch.equal(am.long(), l.argmax(1))
+        m1, _ = _model(True, 1)
+        ls, _ = m1.fused_with_argmax(fd, ad, td if with_text else None)
+        torch.cuda.synchronize()
+        assert (ls - l).abs().max().item() < 1e-3
+        assert (ls.argmax(1) == l.argmax(1)).float().mean().item() >= 0.999
+        m0, _ = _model(True, 0)
+
+
 def test_checkpoint_roundtrip(tmp_path):
     dev = need_gpu()
     m, _ = _model(True, 0)
