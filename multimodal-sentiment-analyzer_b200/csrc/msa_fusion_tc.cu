@@ -567,7 +567,7 @@ __device__ __forceinline__ void prep_short_row(const float* x, const float* gamm
 
 static_assert(kFaceK == 64 && kAudioK == 64, "prep_short_row writes 64 padded columns");
 
-__global__ void __launch_bounds__(256, 3) tc_input_prep_kernel(const PrepArgs a) {
+__global__ void __launch_bounds__(256, 4) tc_input_prep_kernel(const PrepArgs a) {
   // a long row (text, 783 columns) is normalised by one warp with lane-strided columns (coalesced loads), staged as bf16
   // pairs in shared memory and written out 16 bytes per lane: the 2-byte lane-strided stores of the first version ran at
   // a quarter of the HBM rate.
