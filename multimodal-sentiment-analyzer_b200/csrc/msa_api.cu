@@ -9,7 +9,7 @@ void reset_launches() { g_launches = 0; }
 void note_launches(int n) { g_launches += n; }
 }  // namespace msa
 
-extern "C" int msa_version(void) { return 206; }   // 2xx: round 2 (tensor-core STFT-512 round trip)
+extern "C" int msa_version(void) { return 207; }   // 2xx: round 2 (tensor-core STFT-512 round trip)
 extern "C" int msa_last_launch_count(void) { return msa::g_launches; }
 
 extern "C" const char* msa_strerror(int code) {
